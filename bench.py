@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of the SPH time step (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one full SPH step (grid build -> density/pressure -> forces -> walls+integration) over
+the whole scene.  N=1 workload: dam break, box 3.62 -> 1,011,240 particles (BASELINE configs[2]).
+
+* value  : whole-job particle-steps/s, state resident in HBM, timed with CUDA events on the stream
+           the kernels are launched on (sph_step), L2 evicted before every timed step;
+* e2e    : the same metric through the reference-facing plugin (CCUDAParticleSimulator::step) in
+           RoundTrip mirror mode: every step uploads the 80-byte AoS host mirror, steps, and reads it
+           back — the host<->device traffic of the reference's OpenCL path;
+* roofline / cpu_baseline / clocks / gpu_launches as the driver contract asks.
+
+--impl reference times the CPU oracle (a faithful single-threaded restatement of the reference's
+CCPUParticleSimulator; the reference itself needs Qt5+OpenCL and cannot be built) on the host.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "particle_steps_per_sec"
+UNIT = "particle-steps/s"
+ALG_BYTES_PER_PARTICLE_STEP = 260.0
+KERNEL_ALG_BYTES = {"grid": 100.0, "density": 24.0, "forces": 56.0, "integrate": 80.0}  # per particle, §8d (+8 B cell arrays in grid)
+WORKLOADS = {
+    # name: (box, particles)
+    "dam_break_1M": ((3.62, 3.62, 3.62), 1011240),
+    "dam_break_250K": ((2.28, 2.28, 2.28), 250000),
+    "dam_break_32K": ((1.14, 1.14, 1.14), 32500),
+    "dam_break_16K": ((0.9, 0.9, 0.9), 16000),
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle (port of CCPUParticleSimulator) on the host cores; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle_binding import Oracle, build_oracle
+
+    build_oracle()
+    # bounded sample: the largest dam-break scene whose K+W steps fit in ~150 s of single-thread CPU time
+    budget = 150.0 / max(args.steps + args.warmup, 1)
+    per_particle_step = 3.3e-6
+    name = "dam_break_16K"
+    for cand in ("dam_break_1M", "dam_break_250K", "dam_break_32K", "dam_break_16K"):
+        if WORKLOADS[cand][1] * per_particle_step <= budget:
+            name = cand
+            break
+    box, n = WORKLOADS[name]
+    o = Oracle(box).setup_scene()
+    o.step(args.warmup)
+    t0 = time.perf_counter()
+    phase = o.step(args.steps)
+    sec = time.perf_counter() - t0
+    value = o.n * args.steps / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "dam_break_1M", "sample": name, "particles": o.n,
+                   "note": "CPU oracle = single-threaded port of the reference's CCPUParticleSimulator (reference needs Qt5+OpenCL, unbuildable here)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{name}: {o.n} particles x {args.steps} steps from the initial lattice (after {args.warmup} warm-up steps)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "phase_ms": dict(zip(["grid", "density", "forces", "collisions", "integrate"], (phase / args.steps).tolist())),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(pos, vel, box, seconds=12.0):
+    """Oracle timed on a bounded sample of the SAME state the GPU is benchmarked on."""
+    from oracle_binding import Oracle
+
+    o = Oracle(box).set_state(pos, vel)
+    o.step(1)  # first step also pays the initial grid fill from cell 0
+    n_steps = max(1, int(seconds / (o.n * 3.3e-6)))
+    t0 = time.perf_counter()
+    o.step(n_steps)
+    sec = time.perf_counter() - t0
+    return {"value": o.n * n_steps / sec, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{o.n} particles (the benchmarked state) x {n_steps} step(s), oracle single-threaded like the reference CPU path"}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import gmu_water_simulation_b200 as gws
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this benchmark has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    workload = args.workload
+    box, _ = WORKLOADS[workload]
+    sim = gws.Simulator("cuda", box, device=local).setup_scene()
+    ctx = sim.context()
+    n = sim.n
+    if args.density_variant is not None:
+        ctx.set_option("density_variant", args.density_variant)
+    if args.forces_variant is not None:
+        ctx.set_option("forces_variant", args.forces_variant)
+
+    # ---- pre-roll so the dam has collapsed and the state is irregular, then warm-up
+    sim.step_many(1, timed=False)
+    sim.step_many(max(args.preroll - 1, 1), timed=False)
+    ctx.synchronize()
+    ctx.set_option("flush_l2", 1 if args.flush_l2 else 0)
+    sim.step_many(max(args.warmup, 3))
+
+    # ---- timed region: exactly K steps, device time from CUDA events on the launching stream
+    launches0 = ctx.counter("kernel_launches")
+    barrier()
+    with ClockSampler(local) as clocks:
+        wall0 = time.perf_counter()
+        dev_ms = sim.step_many(args.steps)
+        barrier()
+        wall = time.perf_counter() - wall0
+        if wall < 1.5:  # keep the GPU under the same load long enough for a few clock samples
+            ctx.set_option("flush_l2", 0)
+            t_end = time.perf_counter() + 1.5
+            while time.perf_counter() < t_end:
+                sim.step_many(50, timed=True)
+            ctx.set_option("flush_l2", 1 if args.flush_l2 else 0)
+    launches = ctx.counter("kernel_launches") - launches0
+    dev_ms = max_over_ranks(dev_ms)
+    total_particles = sum_over_ranks(float(n))
+    value = total_particles * args.steps / (dev_ms * 1e-3)
+
+    # ---- same loop with a warm L2 (no eviction), for information
+    ctx.set_option("flush_l2", 0)
+    sim.step_many(3)
+    warm_ms = max_over_ranks(sim.step_many(args.steps))
+
+    # ---- per-kernel split with CUDA events around each phase (C ABI phase calls), L2 evicted per step
+    phase_ms = {"grid": 0.0, "density": 0.0, "forces": 0.0, "integrate": 0.0}
+    reps = min(args.steps, 20)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(reps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        phase_ms["grid"] += ctx.update_grid()
+        phase_ms["density"] += ctx.density_pressure()
+        phase_ms["forces"] += ctx.forces()
+        ctx.collisions()
+        phase_ms["integrate"] += ctx.integrate()
+    phase_ms = {k: v / reps for k, v in phase_ms.items()}
+    ctx.update_grid(); ctx.density_pressure()
+    nb_counts, _ = ctx.neighbours(lists=False)
+    ctx.forces(); ctx.integrate()
+    mean_nb = float(nb_counts.mean())
+
+    peak, peak_src = measured_peaks()
+    top = max(("density", "forces"), key=lambda k: phase_ms[k])
+    top_bytes = KERNEL_ALG_BYTES[top] * n
+    top_gbs = top_bytes / (phase_ms[top] * 1e-3) / 1e9
+    step_gbs = value / world * ALG_BYTES_PER_PARTICLE_STEP / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": f"k_{top}", "achieved": top_gbs, "peak": peak, "unit": "GB/s", "frac": top_gbs / peak,
+        "traffic": None, "peak_source": peak_src,
+        "alg_bytes_per_launch": top_bytes,
+        "kernel_ms": phase_ms[top],
+        "step_level": {"alg_bytes_per_particle_step": ALG_BYTES_PER_PARTICLE_STEP, "achieved": step_gbs, "frac": step_gbs / peak},
+        "note": "neighbour kernels are fp32-issue/L1 bound, not HBM bound (SURVEY.md §8d); see profiles/",
+    }
+
+    # ---- end to end through the plugin: upload AoS mirror + step + download, every step
+    e2e = None
+    if rank == 0 or world > 1:
+        sim.set_mirror_mode(2)
+        sim.step(2)
+        barrier()
+        t0 = time.perf_counter()
+        sim.step(args.e2e_steps)
+        barrier()
+        e2e_sec = max_over_ranks(time.perf_counter() - t0)
+        sim.set_mirror_mode(0)
+        e2e = {"value": total_particles * args.e2e_steps / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": 80 * n * world,
+               "d2h_bytes_per_step": 80 * n * world, "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_sec / args.e2e_steps,
+               "path": "CCUDAParticleSimulator::step(), MirrorMode::RoundTrip (pinned 80-byte AoS host mirror up and down every step)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sim.sync_host()
+        hp = sim.host_particles()
+        cpu = cpu_baseline_sample(hp["position"][:, :3].copy(), hp["velocity"][:, :3].copy(), box, args.cpu_seconds)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "particles_per_gpu": n, "box": list(box), "grid": list(ctx.grid_res),
+                       "preroll_steps": args.preroll, "mean_neighbours": mean_nb,
+                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (slab mode pending)",
+                       "l2": "L2 evicted (256 MiB scratch write) before every timed step" if args.flush_l2 else "no eviction"},
+            "clocks": clocks.summary(),
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "phase_ms": phase_ms,
+            "value_warm_l2": total_particles * args.steps / (warm_ms * 1e-3),
+            "wall_ms_per_step": 1e3 * wall / args.steps,
+            "device": sim.device,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="dam_break_1M", choices=sorted(WORKLOADS))
+    ap.add_argument("--preroll", type=int, default=200)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")
+    ap.add_argument("--density-variant", type=int, default=None)
+    ap.add_argument("--forces-variant", type=int, default=None)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

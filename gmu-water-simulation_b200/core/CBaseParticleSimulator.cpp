@@ -1,0 +1,143 @@
+// CBaseParticleSimulator.cpp — scene setup, emission, phase sequencing (headless).
+// Behaviour follows src/CBaseParticleSimulator.cpp of the reference; the fp32/fp64 mix of the lattice
+// loops is kept exactly because step-0 neighbour sets depend on the accumulated fp32 coordinates.
+#include "CBaseParticleSimulator.h"
+
+#include <cassert>
+#include <cmath>
+
+CBaseParticleSimulator::CBaseParticleSimulator(CScene *scene, float boxSize, SimulationScenario scenario, QObject *parent)
+    : CBaseParticleSimulator(scene, QVector3D(boxSize, boxSize, boxSize), scenario, parent) {}
+
+CBaseParticleSimulator::CBaseParticleSimulator(CScene *scene, QVector3D boxSize, SimulationScenario scenario, QObject *parent)
+    : QObject(parent), m_scenario(scenario), m_scene(scene), gravity(0, GRAVITY_ACCELERATION, 0), dt(0.01f),
+      m_grid(nullptr), m_boxSize(boxSize), m_surfaceThreshold(0.01f) {
+    // kernel constants in fp32, as the reference stores them for its device code (:23-25)
+    const double h = CParticle::h;
+    m_systemParams.poly6_constant = (cl_float)(315.0f / (64.0f * M_PI * std::pow(h, 9)));
+    m_systemParams.spiky_constant = (cl_float)(-45.0f / (M_PI * std::pow(h, 6)));
+    m_systemParams.viscosity_constant = (cl_float)(45.0f / (M_PI * std::pow(h, 6)));
+
+    // ceil(box / h) per axis with a float division (:27-31)
+    const QVector3D resolution((float)(int)std::ceil(m_boxSize.x() / CParticle::h),
+                               (float)(int)std::ceil(m_boxSize.y() / CParticle::h),
+                               (float)(int)std::ceil(m_boxSize.z() / CParticle::h));
+    m_grid = new CGrid(m_boxSize, resolution);
+}
+
+void CBaseParticleSimulator::setupScene() {
+    // :38-65.  halfParticle is a double holding the fp32 value h/2; the loop variables are fp32
+    // accumulators ("y += halfParticle" rounds to fp32 on every add).
+    const double halfParticle = CParticle::h / 2.0f;
+    const unsigned int calculatedCount =
+        (unsigned)(std::ceil(m_boxSize.z() / halfParticle) * std::ceil(m_boxSize.y() / halfParticle) *
+                   std::ceil(m_boxSize.x() / 4 / halfParticle));
+    m_clParticles.reserve(calculatedCount);
+
+    if (m_scenario == DAM_BREAK) {
+        const QVector3D offset = -m_boxSize / 2.0f;
+        for (float y = 0; y < m_boxSize.y(); y += halfParticle)
+            for (float x = 0; x < m_boxSize.x() / 4.0; x += halfParticle)
+                for (float z = 0; z < m_boxSize.z(); z += halfParticle)
+                    addParticle(x + offset.x(), y + offset.y(), z + offset.z());
+        assert(calculatedCount == (unsigned)m_particlesCount);
+        m_maxParticlesCount = (cl_uint)m_particlesCount;
+    } else {
+        m_maxParticlesCount = calculatedCount;
+    }
+}
+
+void CBaseParticleSimulator::addParticle(float x, float y, float z, cl_float3 initialVelocity) {
+    // :67-74 without the per-particle Qt3D entity
+    m_clParticles.emplace_back(x, y, z, (cl_uint)m_particlesCount, initialVelocity);
+    m_particlesCount++;
+}
+
+void CBaseParticleSimulator::generateParticles() {
+    // :187-210 — seven particles per nozzle per step at the box floor, shot upwards
+    if (m_scenario != FOUNTAIN) return;
+    const int particlesPerIteration = 7;
+    const float halfParticle = CParticle::h / 2.0f;
+    const QVector3D offset = -m_boxSize / 2.0f;
+    const cl_float3 initialVelocity = {0.0f, m_boxSize.y() * 3.2f, 0.0f, 0.0f};
+    for (int nozzle = 0; nozzle < m_emissionMultiplier; ++nozzle) {
+        if ((cl_uint)m_particlesCount >= (m_maxParticlesCount - (cl_uint)particlesPerIteration)) return;
+        // one nozzle sits at the origin like the reference's; with more nozzles (extension) they form a
+        // centred square array 3h apart so their particles never coincide
+        const int side = (int)std::ceil(std::sqrt((double)m_emissionMultiplier));
+        const float cx = 3.0f * CParticle::h * ((float)(nozzle % side) - 0.5f * (float)(side - 1));
+        const float cz = 3.0f * CParticle::h * ((float)(nozzle / side) - 0.5f * (float)(side - 1));
+        addParticle(cx + 0, offset.y(), cz + 0, initialVelocity);
+        addParticle(cx + -halfParticle, offset.y(), cz + 0, initialVelocity);
+        addParticle(cx + halfParticle, offset.y(), cz + 0, initialVelocity);
+        addParticle(cx + -CParticle::h / 4, offset.y(), cz + -halfParticle, initialVelocity);
+        addParticle(cx + CParticle::h / 4, offset.y(), cz + -halfParticle, initialVelocity);
+        addParticle(cx + -CParticle::h / 4, offset.y(), cz + halfParticle, initialVelocity);
+        addParticle(cx + CParticle::h / 4, offset.y(), cz + halfParticle, initialVelocity);
+    }
+}
+
+void CBaseParticleSimulator::start() {
+    iterationSincePaused = 0;
+    m_timer.start();
+    m_elapsed_timer.start();
+}
+
+void CBaseParticleSimulator::stop() { m_timer.stop(); }
+
+void CBaseParticleSimulator::toggleSimulation() {
+    if (m_timer.isActive()) {
+        m_timer.stop();
+    } else {
+        m_elapsed_timer.restart();
+        start();
+    }
+}
+
+void CBaseParticleSimulator::toggleGravity() {
+    if (gravity.length() > 0.0)
+        setGravityVector(QVector3D(0, 0, 0));
+    else
+        setGravityVector(QVector3D(0, GRAVITY_ACCELERATION, 0));
+}
+
+void CBaseParticleSimulator::setGravityVector(QVector3D newGravity) { gravity = newGravity; }
+
+void CBaseParticleSimulator::step() {
+    // :116-144 — emit, then the five phases; durations are logged every eventLoggerStride-th step
+    sProfilingEvent durations(totalIteration);
+    generateParticles();
+    durations.updateGrid = updateGrid();
+    durations.updateDensityPressure = updateDensityPressure();
+    durations.updateForces = updateForces();
+    durations.updateCollisions = updateCollisions();
+    durations.integrate = integrate();
+    if (sampleThisStep()) {
+        durations.fps = getFps();
+        events << durations;
+    }
+}
+
+void CBaseParticleSimulator::doWork() {
+    this->step();
+    ++totalIteration;
+    ++iterationSincePaused;
+    emitIterationChanged(totalIteration);
+}
+
+void CBaseParticleSimulator::onKeyPressed(Qt::Key key) {
+    // :154-179
+    switch (key) {
+        case Qt::Key_S: doWork(); break;
+        case Qt::Key_Space: toggleSimulation(); break;
+        case Qt::Key_G: toggleGravity(); break;
+        case Qt::Key_O: gravity.setX(gravity.x() - 1); setGravityVector(gravity); break;
+        case Qt::Key_P: gravity.setX(gravity.x() + 1); setGravityVector(gravity); break;
+        default: break;
+    }
+}
+
+double CBaseParticleSimulator::getFps() {
+    const double elapsed = getElapsedTime() / 1000.0;
+    return elapsed > 0 ? iterationSincePaused / elapsed : 0.0;
+}

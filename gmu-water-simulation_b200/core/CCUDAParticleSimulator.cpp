@@ -1,0 +1,128 @@
+// CCUDAParticleSimulator.cpp — host side of the CUDA simulator: scene upload, phase calls through the
+// C ABI, error propagation as in CGPUBaseParticleSimulator (src/CGPUBaseParticleSimulator.cpp:28-37).
+#include "CCUDAParticleSimulator.h"
+
+#include <cstring>
+
+static_assert(sizeof(CParticle::Physics) == sizeof(sph_particle), "host mirror record != ABI record");
+
+CCUDAParticleSimulator::CCUDAParticleSimulator(CScene *scene, float boxSize, int device, SimulationScenario scenario, QObject *parent)
+    : CBaseParticleSimulator(scene, boxSize, scenario, parent), m_device(device) {}
+
+CCUDAParticleSimulator::CCUDAParticleSimulator(CScene *scene, QVector3D boxSize, int device, SimulationScenario scenario, QObject *parent)
+    : CBaseParticleSimulator(scene, boxSize, scenario, parent), m_device(device) {}
+
+CCUDAParticleSimulator::~CCUDAParticleSimulator() = default;
+
+QString CCUDAParticleSimulator::getSelectedDevice() { return CUDAPlatforms::getDeviceInfo(m_device); }
+
+void CCUDAParticleSimulator::setGravityVector(QVector3D newGravity) {
+    CBaseParticleSimulator::setGravityVector(newGravity);
+    if (m_cuda) m_cuda->check(sph_set_gravity(m_cuda->ctx(), gravity.x(), gravity.y(), gravity.z()), "setGravityVector");
+}
+
+void CCUDAParticleSimulator::setupScene() {
+    CBaseParticleSimulator::setupScene();  // fills m_clParticles / m_maxParticlesCount
+
+    // ≙ CGPUBaseParticleSimulator::setupKernels: size the device buffers, hand over walls and constants
+    sph_config cfg;
+    sph_config_init(&cfg, m_boxSize.x(), m_boxSize.y(), m_boxSize.z(), m_maxParticlesCount > 0 ? m_maxParticlesCount : 1);
+    cfg.grid_res[0] = m_grid->xRes();
+    cfg.grid_res[1] = m_grid->yRes();
+    cfg.grid_res[2] = m_grid->zRes();
+    cfg.dt = dt;
+    cfg.gravity[0] = gravity.x();
+    cfg.gravity[1] = gravity.y();
+    cfg.gravity[2] = gravity.z();
+    const auto &walls = m_grid->getCollisionGeometry()->getBoundingBox().m_walls;
+    cfg.wall_count = (int32_t)walls.size();
+    std::memcpy(cfg.walls, walls.data(), walls.size() * sizeof(sWall));
+    cfg.device = m_device;
+    m_cuda.reset(new CUDAWrapper(cfg));
+
+    // page-lock the host mirror once: it never reallocates (reserved to the maximum count in setupScene)
+    if (m_clParticles.capacity() > 0)
+        sph_pin_host_buffer(m_cuda->ctx(), m_clParticles.data(), m_clParticles.capacity() * sizeof(CParticle::Physics));
+
+    m_deviceCount = 0;
+    m_cuda->check(sph_upload_particles(m_cuda->ctx(), reinterpret_cast<const sph_particle *>(m_clParticles.data()),
+                                       (uint32_t)m_particlesCount), "setupScene upload");
+    m_deviceCount = (cl_uint)m_particlesCount;
+}
+
+void CCUDAParticleSimulator::pushNewParticles() {
+    // fountain: generateParticles() appended to the host mirror; send only the new tail
+    if ((cl_uint)m_particlesCount > m_deviceCount) {
+        m_cuda->check(sph_append_particles(m_cuda->ctx(), reinterpret_cast<const sph_particle *>(m_clParticles.data()) + m_deviceCount,
+                                           (uint32_t)m_particlesCount - m_deviceCount), "append");
+        m_deviceCount = (cl_uint)m_particlesCount;
+    }
+}
+
+void CCUDAParticleSimulator::step() {
+    try {
+        if (m_mirrorMode == RoundTrip && m_cuda) {
+            m_cuda->check(sph_upload_particles(m_cuda->ctx(), reinterpret_cast<const sph_particle *>(m_clParticles.data()),
+                                               m_deviceCount), "step upload");
+        }
+        CBaseParticleSimulator::step();
+        if (m_mirrorMode != Resident) syncHostMirror();
+    } catch (CUDAException &exc) {
+        emitErrorOccured(exc.what());
+        stop();
+    }
+}
+
+void CCUDAParticleSimulator::stepMany(int steps, double *deviceMs) {
+    if (!m_cuda) throw CUDAException("stepMany before setupScene");
+    if (m_scenario == FOUNTAIN || m_brute) {  // emission / all-pairs go through the phase path
+        for (int k = 0; k < steps; ++k) { CBaseParticleSimulator::step(); addIterations(1); }
+        if (deviceMs) { m_cuda->check(sph_synchronize(m_cuda->ctx()), "stepMany"); *deviceMs = 0.0; }
+        return;
+    }
+    m_cuda->check(sph_step(m_cuda->ctx(), steps, deviceMs), "stepMany");
+    addIterations((unsigned long)steps);
+}
+
+void CCUDAParticleSimulator::syncHostMirror() {
+    uint32_t n = 0;
+    m_cuda->check(sph_download_particles(m_cuda->ctx(), reinterpret_cast<sph_particle *>(m_clParticles.data()),
+                                         (uint32_t)m_clParticles.size(), &n), "syncHostMirror");
+}
+
+// Phase durations are only measured (which forces a device sync) on the steps the profiler samples;
+// otherwise the phases are enqueued asynchronously and report 0, like the reference with PROFILING off.
+double CCUDAParticleSimulator::updateGrid() {
+    pushNewParticles();
+    double ms = 0.0;
+    if (m_brute) return 0.0;  // ≙ CGPUBruteParticleSimulator::updateGrid: nothing to build
+    m_cuda->check(sph_update_grid(m_cuda->ctx(), sampleThisStep() ? &ms : nullptr), "updateGrid");
+    return ms;
+}
+
+double CCUDAParticleSimulator::updateDensityPressure() {
+    double ms = 0.0;
+    double *out = sampleThisStep() ? &ms : nullptr;
+    m_cuda->check(m_brute ? sph_brute_density_pressure(m_cuda->ctx(), out) : sph_density_pressure(m_cuda->ctx(), out),
+                  "updateDensityPressure");
+    return ms;
+}
+
+double CCUDAParticleSimulator::updateForces() {
+    double ms = 0.0;
+    double *out = sampleThisStep() ? &ms : nullptr;
+    m_cuda->check(m_brute ? sph_brute_forces(m_cuda->ctx(), out) : sph_forces(m_cuda->ctx(), out), "updateForces");
+    return ms;
+}
+
+double CCUDAParticleSimulator::updateCollisions() {
+    double ms = 0.0;
+    m_cuda->check(sph_collisions(m_cuda->ctx(), &ms), "updateCollisions");
+    return ms;
+}
+
+double CCUDAParticleSimulator::integrate() {
+    double ms = 0.0;
+    m_cuda->check(sph_integrate(m_cuda->ctx(), sampleThisStep() ? &ms : nullptr), "integrate");
+    return ms;
+}

@@ -1,0 +1,747 @@
+// sph_capi.cu — the C ABI of include/sph_cuda.h: context, buffers, phase sequencing, CUDA-graph step,
+// event timing and error strings.  Replaces CLWrapper (src/CLWrapper.cpp) and CLPlatforms
+// (src/CLPlatforms.cpp) for the SPH path.  No CPU fallback anywhere: without a usable CUDA device
+// every entry point returns SPH_ERR_CUDA.
+#include "../../include/sph_cuda.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sph_kernels.h"
+
+using namespace sph;
+
+static_assert(sizeof(sph_particle) == 80, "sph_particle must match CParticle::Physics (80 B)");
+static_assert(sizeof(ParticleAoS) == 80, "ParticleAoS must match sph_particle");
+static_assert(sizeof(sph_wall) == 32, "sph_wall must match sWall (32 B)");
+
+namespace {
+thread_local std::string g_last_error;  // for failures without a context
+}
+
+struct sph_context {
+    sph_config cfg;
+    Params P;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t cap = 0, n = 0;
+    // A = authoritative state (pos/vel), S = canonical-order snapshot the neighbour passes read
+    float4 *pos_a = nullptr, *vel_a = nullptr, *pos_s = nullptr, *vel_s = nullptr;
+    float4 *dp = nullptr, *acc = nullptr;
+    int *nb_count = nullptr;
+    GridBuffers g{};
+    size_t cells_padded = 0;
+    bool s_valid = false;     // S holds the pre-integration snapshot the aux arrays are aligned with
+    bool grid_valid = false;  // S is in canonical order, key_s / cell_start valid
+    bool a_aligned = false;   // A is in the same order as S (true after integrate)
+    bool density_valid = false, forces_valid = false;
+    ParticleAoS *d_stage = nullptr;
+    size_t stage_cap = 0;
+    int *d_tmp_i32 = nullptr;  // [cap] scratch for by-id taps
+    float *d_tmp_f32 = nullptr;  // [5*cap]
+    double *d_stats = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    uint32_t graph_n = 0;
+    uint32_t last_step_n = 0xffffffffu;
+    int opt_density_variant = 0, opt_forces_variant = 0, opt_use_graph = 1, opt_count_neighbours = 1;
+    uint64_t kernel_launches = 0, graph_launches = 0, steps = 0;
+    std::string err;
+    void *pinned_ptr = nullptr;
+    // bench hygiene: evict L2 between timed steps (option "flush_l2") and time each step separately
+    int opt_flush_l2 = 0;
+    float4 *d_flush = nullptr;
+    size_t flush_count = 0;
+    std::vector<cudaEvent_t> step_events;
+};
+
+namespace {
+
+int fail(sph_context *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(ctx, call)                                                                                   \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(ctx, SPH_ERR_CUDA,                                                                    \
+                        std::string("CUDA::") + cudaGetErrorName(e_) + ": " + cudaGetErrorString(e_) + " | " #call); \
+    } while (0)
+
+#define REQUIRE(ctx, cond, code, msg) \
+    do {                              \
+        if (!(cond)) return fail(ctx, code, msg); \
+    } while (0)
+
+int check_launch(sph_context *ctx, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, SPH_ERR_CUDA, std::string("CUDA::") + cudaGetErrorName(e) + " after " + what);
+    return SPH_OK;
+}
+
+Params make_params(const sph_config &c) {
+    Params P{};
+    P.rx = c.grid_res[0];
+    P.ry = c.grid_res[1];
+    P.rz = c.grid_res[2];
+    P.n_cells = P.rx * P.ry * P.rz;
+    // src/CCPUParticleSimulator.cpp:46-48: m_boxSize.x() / 2.0 and CParticle::h widen to double
+    P.hbx = (double)c.box[0] / 2.0;
+    P.hby = (double)c.box[1] / 2.0;
+    P.hbz = (double)c.box[2] / 2.0;
+    P.h_d = (double)c.h;
+    P.h = c.h;
+    P.h2 = c.h * c.h;  // fp32 product, as CParticle::h * CParticle::h
+    P.dt = c.dt;
+    P.mass = c.mass;
+    P.viscosity = c.viscosity;
+    P.gas_stiffness = c.gas_stiffness;
+    P.rest_density = c.rest_density;
+    // fp64 coefficients of the CPU path (src/CCPUParticleSimulator.cpp:11,19,26), rounded once
+    const double pi = 3.14159265358979323846;
+    P.poly6_f = (float)(315.0 / (64.0 * pi * std::pow((double)c.h, 9)));
+    P.spiky_f = (float)(-45.0 / (pi * std::pow((double)c.h, 6)));
+    P.visc_f = (float)(45.0 / (pi * std::pow((double)c.h, 6)));
+    P.gx = c.gravity[0];
+    P.gy = c.gravity[1];
+    P.gz = c.gravity[2];
+    P.wall_k_f = c.wall_k;
+    P.wall_damping_d = (double)c.wall_damping;
+    P.wall_skin_d = (double)c.wall_skin;
+    P.wall_count = c.wall_count;
+    for (int w = 0; w < 6; ++w) {
+        P.walls[w] = {c.walls[w].normal[0],   c.walls[w].normal[1],   c.walls[w].normal[2],
+                      c.walls[w].position[0], c.walls[w].position[1], c.walls[w].position[2]};
+    }
+    return P;
+}
+
+template <typename T>
+cudaError_t dalloc(T **p, size_t count) {
+    return cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(count, 1) * sizeof(T));
+}
+
+struct PhaseTimer {
+    sph_context *c;
+    double *ms;
+    PhaseTimer(sph_context *ctx, double *out) : c(ctx), ms(out) {
+        if (ms) cudaEventRecord(c->ev0, c->stream);
+    }
+    int finish() {
+        if (!ms) return SPH_OK;
+        cudaEventRecord(c->ev1, c->stream);
+        cudaError_t e = cudaEventSynchronize(c->ev1);
+        if (e != cudaSuccess) return fail(c, SPH_ERR_CUDA, std::string("CUDA::") + cudaGetErrorName(e) + " in phase");
+        float t = 0.f;
+        cudaEventElapsedTime(&t, c->ev0, c->ev1);
+        *ms = (double)t;
+        return SPH_OK;
+    }
+};
+
+// ---- the pipeline pieces (enqueue only) -------------------------------------------------------
+void enqueue_grid(sph_context *c) {
+    const int n = (int)c->n;
+    launch_cell_key_hist(c->pos_a, n, c->g, c->P, c->stream);
+    launch_scan(c->g, c->stream);
+    launch_bucket(c->pos_a, n, c->g, c->stream);
+    launch_rank_scatter(c->pos_a, c->vel_a, c->pos_s, c->vel_s, n, c->g, c->stream);
+    c->kernel_launches += 4;
+}
+void enqueue_density(sph_context *c) {
+    launch_density(c->pos_s, c->g.key_s, c->g.cell_start, c->dp, c->opt_count_neighbours ? c->nb_count : nullptr,
+                   (int)c->n, c->P, c->opt_density_variant, c->stream);
+    c->kernel_launches += 1;
+}
+void enqueue_forces(sph_context *c) {
+    launch_forces(c->pos_s, c->vel_s, c->dp, c->g.key_s, c->g.cell_start, c->acc, (int)c->n, c->P,
+                  c->opt_forces_variant, c->stream);
+    c->kernel_launches += 1;
+}
+void enqueue_integrate(sph_context *c) {
+    launch_integrate_collide(c->pos_s, c->vel_s, c->acc, c->pos_a, c->vel_a, (int)c->n, c->P, c->stream);
+    c->kernel_launches += 1;
+}
+void enqueue_step(sph_context *c) {
+    enqueue_grid(c);
+    enqueue_density(c);
+    enqueue_forces(c);
+    enqueue_integrate(c);
+}
+constexpr int kKernelsPerStep = 7;
+
+void drop_graph(sph_context *c) {
+    if (c->graph_exec) {
+        cudaGraphExecDestroy(c->graph_exec);
+        c->graph_exec = nullptr;
+    }
+    c->graph_n = 0;
+}
+
+// pos/vel arrays the taps should read: S between update_grid and integrate, A otherwise
+const float4 *view_pos(const sph_context *c) { return c->a_aligned || !c->s_valid ? c->pos_a : c->pos_s; }
+const float4 *view_vel(const sph_context *c) { return c->a_aligned || !c->s_valid ? c->vel_a : c->vel_s; }
+bool aux_aligned(const sph_context *c) { return c->s_valid; }  // dp/acc/key_s index == view index
+
+}  // namespace
+
+extern "C" {
+
+int sph_abi_version(void) { return SPH_ABI_VERSION; }
+
+int sph_device_count(int *count) {
+    REQUIRE(nullptr, count, SPH_ERR_ARGUMENT, "sph_device_count: count is NULL");
+    *count = 0;
+    CUDA_TRY(nullptr, cudaGetDeviceCount(count));
+    return SPH_OK;
+}
+
+int sph_device_name(int device, char *buf, size_t len) {
+    REQUIRE(nullptr, buf && len > 0, SPH_ERR_ARGUMENT, "sph_device_name: empty buffer");
+    cudaDeviceProp prop;
+    CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+    std::snprintf(buf, len, "%s (CUDA sm_%d%d, %d SMs, %.0f GB)", prop.name, prop.major, prop.minor,
+                  prop.multiProcessorCount, (double)prop.totalGlobalMem / 1e9);
+    return SPH_OK;
+}
+
+int sph_config_init(sph_config *cfg, float bx, float by, float bz, uint32_t max_particles) {
+    REQUIRE(nullptr, cfg, SPH_ERR_ARGUMENT, "sph_config_init: cfg is NULL");
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->box[0] = bx;
+    cfg->box[1] = by;
+    cfg->box[2] = bz;
+    cfg->h = 0.0457f;             // include/CParticle.h:80
+    cfg->viscosity = 3.5f;        // :81
+    cfg->mass = 0.02f;            // :82
+    cfg->gas_stiffness = 3.0f;    // :83
+    cfg->rest_density = 998.29f;  // :84
+    cfg->dt = 0.01f;              // src/CBaseParticleSimulator.cpp:7
+    for (int a = 0; a < 3; ++a) cfg->grid_res[a] = (int)std::ceil(cfg->box[a] / cfg->h);  // :27-31 (float division)
+    cfg->gravity[1] = -9.80665f;  // include/CBaseParticleSimulator.h:19
+    cfg->wall_k = 10000.0f;       // include/CCollisionGeometry.h:20
+    cfg->wall_damping = -0.9f;    // :21 (exact value used: the double -0.9, see Params)
+    cfg->wall_skin = 0.01f;
+    cfg->wall_count = 6;
+    const float mn[3] = {-(bx / 2.0f), -(by / 2.0f), -(bz / 2.0f)}, mx[3] = {bx / 2.0f, by / 2.0f, bz / 2.0f};
+    for (int a = 0; a < 3; ++a) {  // include/CCollisionGeometry.h:79-120
+        cfg->walls[a].normal[a] = -1.0f;
+        cfg->walls[a].position[a] = mn[a];
+        cfg->walls[a + 3].normal[a] = 1.0f;
+        cfg->walls[a + 3].position[a] = mx[a];
+    }
+    cfg->max_particles = max_particles;
+    cfg->device = 0;
+    cfg->rank = 0;
+    cfg->world = 1;
+    return SPH_OK;
+}
+
+int sph_destroy(sph_context *c) {
+    if (!c) return SPH_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    drop_graph(c);
+    void *ptrs[] = {c->pos_a, c->vel_a, c->pos_s, c->vel_s, c->dp, c->acc, c->nb_count, c->g.key_a, c->g.off_a,
+                    c->g.bucket_src, c->g.bucket_id, c->g.key_s, c->g.count, c->g.cell_start, c->g.scan_status,
+                    c->d_stage, c->d_tmp_i32, c->d_tmp_f32, c->d_stats};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (c->d_flush) cudaFree(c->d_flush);
+    for (cudaEvent_t e : c->step_events) cudaEventDestroy(e);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->pinned_ptr) cudaHostUnregister(c->pinned_ptr);
+    delete c;
+    return SPH_OK;
+}
+
+int sph_create(const sph_config *cfg, sph_context **out) {
+    REQUIRE(nullptr, cfg && out, SPH_ERR_ARGUMENT, "sph_create: NULL argument");
+    *out = nullptr;
+    REQUIRE(nullptr, cfg->grid_res[0] > 0 && cfg->grid_res[1] > 0 && cfg->grid_res[2] > 0, SPH_ERR_ARGUMENT,
+            "sph_create: grid resolution must be positive");
+    REQUIRE(nullptr, (double)cfg->grid_res[0] * cfg->grid_res[1] * cfg->grid_res[2] < 2.0e9, SPH_ERR_ARGUMENT,
+            "sph_create: too many cells for 32-bit keys");
+    REQUIRE(nullptr, cfg->max_particles > 0 && cfg->max_particles < 0x7fffff00u, SPH_ERR_ARGUMENT,
+            "sph_create: max_particles out of range");
+    REQUIRE(nullptr, cfg->wall_count >= 0 && cfg->wall_count <= 6, SPH_ERR_ARGUMENT, "sph_create: wall_count > 6");
+    REQUIRE(nullptr, cfg->world <= 1, SPH_ERR_ARGUMENT, "sph_create: slab mode is created through sph_slab_create");
+    int count = 0;
+    CUDA_TRY(nullptr, cudaGetDeviceCount(&count));
+    REQUIRE(nullptr, cfg->device >= 0 && cfg->device < count, SPH_ERR_CUDA, "sph_create: no such CUDA device");
+    CUDA_TRY(nullptr, cudaSetDevice(cfg->device));
+
+    sph_context *c = new sph_context();
+    c->cfg = *cfg;
+    c->device = cfg->device;
+    c->P = make_params(*cfg);
+    c->cap = cfg->max_particles;
+    const size_t cap = c->cap;
+    const size_t items = (size_t)c->P.n_cells + 1;
+    c->g.n_scan_items = (int)items;
+    c->g.n_tiles = (int)((items + kScanTile - 1) / kScanTile);
+    c->cells_padded = (size_t)c->g.n_tiles * kScanTile;
+
+#define CTX_TRY(call)                       \
+    do {                                    \
+        cudaError_t e_ = (call);            \
+        if (e_ != cudaSuccess) {            \
+            std::string m = std::string("CUDA::") + cudaGetErrorName(e_) + " | " #call; \
+            sph_destroy(c);                 \
+            return fail(nullptr, SPH_ERR_CUDA, m); \
+        }                                   \
+    } while (0)
+
+    CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CTX_TRY(cudaEventCreate(&c->ev0));
+    CTX_TRY(cudaEventCreate(&c->ev1));
+    CTX_TRY(dalloc(&c->pos_a, cap));
+    CTX_TRY(dalloc(&c->vel_a, cap));
+    CTX_TRY(dalloc(&c->pos_s, cap));
+    CTX_TRY(dalloc(&c->vel_s, cap));
+    CTX_TRY(dalloc(&c->dp, cap));
+    CTX_TRY(dalloc(&c->acc, cap));
+    CTX_TRY(dalloc(&c->nb_count, cap));
+    CTX_TRY(dalloc(&c->g.key_a, cap));
+    CTX_TRY(dalloc(&c->g.off_a, cap));
+    CTX_TRY(dalloc(&c->g.bucket_src, cap));
+    CTX_TRY(dalloc(&c->g.bucket_id, cap));
+    CTX_TRY(dalloc(&c->g.key_s, cap));
+    CTX_TRY(dalloc(&c->g.count, c->cells_padded));
+    CTX_TRY(dalloc(&c->g.cell_start, c->cells_padded));
+    CTX_TRY(dalloc(&c->g.scan_status, (size_t)c->g.n_tiles + 1));
+    CTX_TRY(dalloc(&c->d_tmp_i32, cap));
+    CTX_TRY(dalloc(&c->d_tmp_f32, cap * 5));
+    CTX_TRY(dalloc(&c->d_stats, (size_t)8));
+    c->stage_cap = std::min<size_t>(cap, (size_t)4 << 20);  // <= 4 Mi records (320 MiB) of AoS staging
+    CTX_TRY(dalloc(&c->d_stage, c->stage_cap));
+    CTX_TRY(cudaMemsetAsync(c->g.count, 0, c->cells_padded * sizeof(int), c->stream));
+    CTX_TRY(cudaMemsetAsync(c->g.cell_start, 0, c->cells_padded * sizeof(int), c->stream));
+    CTX_TRY(cudaMemsetAsync(c->acc, 0, cap * sizeof(float4), c->stream));
+    CTX_TRY(cudaMemsetAsync(c->dp, 0, cap * sizeof(float4), c->stream));
+    CTX_TRY(cudaMemsetAsync(c->nb_count, 0, cap * sizeof(int), c->stream));
+    CTX_TRY(cudaStreamSynchronize(c->stream));
+#undef CTX_TRY
+    *out = c;
+    return SPH_OK;
+}
+
+const char *sph_last_error(const sph_context *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+// ---------------------------------------------------------------- state
+static int upload_range(sph_context *c, const sph_particle *aos, uint32_t first, uint32_t count) {
+    for (uint32_t done = 0; done < count;) {
+        const uint32_t chunk = (uint32_t)std::min<size_t>(count - done, c->stage_cap);
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_stage, aos + done, (size_t)chunk * sizeof(sph_particle), cudaMemcpyHostToDevice,
+                                    c->stream));
+        launch_aos_to_soa(c->d_stage, c->pos_a + first + done, c->vel_a + first + done, (int)chunk, c->stream);
+        c->kernel_launches += 1;
+        done += chunk;
+        if (done < count) CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // staging buffer is reused
+    }
+    return check_launch(c, "aos_to_soa");
+}
+
+int sph_upload_particles(sph_context *c, const sph_particle *aos, uint32_t n) {
+    REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    REQUIRE(c, n <= c->cap, SPH_ERR_ARGUMENT, "sph_upload_particles: n exceeds max_particles");
+    REQUIRE(c, aos || n == 0, SPH_ERR_ARGUMENT, "sph_upload_particles: NULL particles");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    c->n = n;
+    c->s_valid = c->grid_valid = c->a_aligned = c->density_valid = c->forces_valid = false;
+    return upload_range(c, aos, 0, n);
+}
+
+int sph_append_particles(sph_context *c, const sph_particle *aos, uint32_t n_new) {
+    REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    REQUIRE(c, (uint64_t)c->n + n_new <= c->cap, SPH_ERR_ARGUMENT, "sph_append_particles: exceeds max_particles");
+    REQUIRE(c, aos || n_new == 0, SPH_ERR_ARGUMENT, "sph_append_particles: NULL particles");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const uint32_t first = c->n;
+    c->n += n_new;
+    // A stays authoritative; the snapshot S and everything derived from it no longer covers all particles
+    c->s_valid = c->grid_valid = c->a_aligned = c->density_valid = c->forces_valid = false;
+    return upload_range(c, aos, first, n_new);
+}
+
+int sph_download_particles(sph_context *c, sph_particle *aos, uint32_t capacity, uint32_t *n_out) {
+    REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    REQUIRE(c, aos && capacity >= c->n, SPH_ERR_ARGUMENT, "sph_download_particles: buffer too small");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const bool aux = aux_aligned(c);
+    for (uint32_t base = 0; base < c->n;) {
+        const uint32_t chunk = (uint32_t)std::min<size_t>(c->n - base, c->stage_cap);
+        launch_soa_to_aos(view_pos(c), view_vel(c), aux ? c->acc : nullptr, aux ? c->dp : nullptr,
+                          (aux && c->grid_valid) ? c->g.key_s : nullptr, c->d_stage, (int)base, (int)chunk, (int)c->n,
+                          c->P, c->stream);
+        c->kernel_launches += 1;
+        CUDA_TRY(c, cudaMemcpyAsync(aos + base, c->d_stage, (size_t)chunk * sizeof(sph_particle), cudaMemcpyDeviceToHost,
+                                    c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        base += chunk;
+    }
+    if (n_out) *n_out = c->n;
+    return check_launch(c, "soa_to_aos");
+}
+
+int sph_particle_count(const sph_context *c, uint32_t *n_out) {
+    if (!c || !n_out) return SPH_ERR_ARGUMENT;
+    *n_out = c->n;
+    return SPH_OK;
+}
+
+int sph_set_gravity(sph_context *c, float gx, float gy, float gz) {
+    REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    c->cfg.gravity[0] = c->P.gx = gx;
+    c->cfg.gravity[1] = c->P.gy = gy;
+    c->cfg.gravity[2] = c->P.gz = gz;
+    drop_graph(c);  // kernel parameters are baked into the graph
+    return SPH_OK;
+}
+
+int sph_pin_host_buffer(sph_context *c, void *ptr, size_t bytes) {
+    REQUIRE(c, c && ptr, SPH_ERR_ARGUMENT, "sph_pin_host_buffer: NULL argument");
+    if (c->pinned_ptr) {
+        cudaHostUnregister(c->pinned_ptr);
+        c->pinned_ptr = nullptr;
+    }
+    CUDA_TRY(c, cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    c->pinned_ptr = ptr;
+    return SPH_OK;
+}
+
+// ---------------------------------------------------------------- phases
+int sph_update_grid(sph_context *c, double *ms) {
+    REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    PhaseTimer t(c, ms);
+    enqueue_grid(c);
+    c->s_valid = c->grid_valid = true;
+    c->a_aligned = c->density_valid = c->forces_valid = false;
+    int rc = check_launch(c, "update_grid");
+    return rc ? rc : t.finish();
+}
+
+int sph_density_pressure(sph_context *c, double *ms) {
+    REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    REQUIRE(c, c->grid_valid && !c->a_aligned, SPH_ERR_STATE, "sph_density_pressure: call sph_update_grid first");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    PhaseTimer t(c, ms);
+    enqueue_density(c);
+    c->density_valid = true;
+    int rc = check_launch(c, "density_pressure");
+    return rc ? rc : t.finish();
+}
+
+int sph_forces(sph_context *c, double *ms) {
+    REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    REQUIRE(c, c->grid_valid && c->density_valid && !c->a_aligned, SPH_ERR_STATE,
+            "sph_forces: call sph_density_pressure first");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    PhaseTimer t(c, ms);
+    enqueue_forces(c);
+    c->forces_valid = true;
+    int rc = check_launch(c, "forces");
+    return rc ? rc : t.finish();
+}
+
+int sph_collisions(sph_context *c, double *ms) {
+    REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    if (ms) *ms = 0.0;  // fused into sph_integrate; the CPU path also reports 0 here
+    return SPH_OK;
+}
+
+int sph_integrate(sph_context *c, double *ms) {
+    REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    REQUIRE(c, c->s_valid && c->forces_valid && !c->a_aligned, SPH_ERR_STATE, "sph_integrate: call sph_forces first");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    PhaseTimer t(c, ms);
+    enqueue_integrate(c);
+    c->a_aligned = true;
+    int rc = check_launch(c, "integrate");
+    return rc ? rc : t.finish();
+}
+
+int sph_step(sph_context *c, int n_steps, double *ms) {
+    REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    REQUIRE(c, n_steps >= 0, SPH_ERR_ARGUMENT, "sph_step: negative step count");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (n_steps == 0 || c->n == 0) {
+        if (ms) *ms = 0.0;
+        return SPH_OK;
+    }
+    // Capture the step once the particle count is stable (a fountain still filling changes n every step).
+    if (c->opt_use_graph && !c->graph_exec && c->last_step_n == c->n) {
+        cudaGraph_t graph = nullptr;
+        const uint64_t launches_before = c->kernel_launches;
+        CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        enqueue_step(c);
+        cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        c->kernel_launches = launches_before;
+        if (e != cudaSuccess) return fail(c, SPH_ERR_CUDA, std::string("CUDA::") + cudaGetErrorName(e) + " in graph capture");
+        e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(c, SPH_ERR_CUDA, std::string("CUDA::") + cudaGetErrorName(e) + " in graph instantiate");
+        c->graph_n = c->n;
+    }
+    if (c->graph_exec && c->graph_n != c->n) drop_graph(c);
+    c->last_step_n = c->n;
+
+    if (c->opt_flush_l2) {
+        // Every step is preceded by a write of a 256 MiB scratch buffer (> 126 MB L2) and timed by its own
+        // event pair; *ms is the sum of the per-step device times, the flushes are outside the timed spans.
+        if (!c->d_flush) {
+            c->flush_count = ((size_t)256 << 20) / sizeof(float4);
+            CUDA_TRY(c, dalloc(&c->d_flush, c->flush_count));
+        }
+        while (c->step_events.size() < (size_t)(2 * n_steps)) {
+            cudaEvent_t e;
+            CUDA_TRY(c, cudaEventCreate(&e));
+            c->step_events.push_back(e);
+        }
+        for (int k = 0; k < n_steps; ++k) {
+            launch_flush_l2(c->d_flush, c->flush_count, c->stream);
+            CUDA_TRY(c, cudaEventRecord(c->step_events[2 * k], c->stream));
+            if (c->graph_exec) {
+                CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, c->stream));
+                c->graph_launches += 1;
+                c->kernel_launches += kKernelsPerStep;
+            } else {
+                enqueue_step(c);
+            }
+            CUDA_TRY(c, cudaEventRecord(c->step_events[2 * k + 1], c->stream));
+        }
+        c->steps += (uint64_t)n_steps;
+        c->s_valid = c->grid_valid = c->density_valid = c->forces_valid = c->a_aligned = true;
+        int rc0 = check_launch(c, "step");
+        if (rc0) return rc0;
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        double total = 0.0;
+        for (int k = 0; k < n_steps; ++k) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, c->step_events[2 * k], c->step_events[2 * k + 1]);
+            total += (double)t;
+        }
+        if (ms) *ms = total;
+        return SPH_OK;
+    }
+
+    PhaseTimer t(c, ms);
+    for (int k = 0; k < n_steps; ++k) {
+        if (c->graph_exec) {
+            CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, c->stream));
+            c->graph_launches += 1;
+            c->kernel_launches += kKernelsPerStep;
+        } else {
+            enqueue_step(c);
+        }
+    }
+    c->steps += (uint64_t)n_steps;
+    c->s_valid = c->grid_valid = c->density_valid = c->forces_valid = c->a_aligned = true;
+    int rc = check_launch(c, "step");
+    return rc ? rc : t.finish();
+}
+
+int sph_synchronize(sph_context *c) {
+    REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SPH_OK;
+}
+
+// ---------------------------------------------------------------- taps
+int sph_download_keys(sph_context *c, int32_t *keys) {
+    REQUIRE(c, c && keys, SPH_ERR_ARGUMENT, "sph_download_keys: NULL argument");
+    REQUIRE(c, c->grid_valid, SPH_ERR_STATE, "sph_download_keys: grid not built");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    launch_scatter_by_id_i32(c->pos_s, c->g.key_s, c->d_tmp_i32, (int)c->n, c->stream);
+    c->kernel_launches += 1;
+    CUDA_TRY(c, cudaMemcpyAsync(keys, c->d_tmp_i32, (size_t)c->n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return check_launch(c, "download_keys");
+}
+
+int sph_download_permutation(sph_context *c, uint32_t *sorted_ids) {
+    REQUIRE(c, c && sorted_ids, SPH_ERR_ARGUMENT, "sph_download_permutation: NULL argument");
+    REQUIRE(c, c->grid_valid, SPH_ERR_STATE, "sph_download_permutation: grid not built");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    launch_extract_ids(c->pos_s, reinterpret_cast<unsigned *>(c->d_tmp_i32), (int)c->n, c->stream);
+    c->kernel_launches += 1;
+    CUDA_TRY(c, cudaMemcpyAsync(sorted_ids, c->d_tmp_i32, (size_t)c->n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return check_launch(c, "download_permutation");
+}
+
+int sph_download_cell_start(sph_context *c, int32_t *cell_start) {
+    REQUIRE(c, c && cell_start, SPH_ERR_ARGUMENT, "sph_download_cell_start: NULL argument");
+    REQUIRE(c, c->grid_valid, SPH_ERR_STATE, "sph_download_cell_start: grid not built");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaMemcpyAsync(cell_start, c->g.cell_start, ((size_t)c->P.n_cells + 1) * sizeof(int),
+                                cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SPH_OK;
+}
+
+int sph_download_density_pressure_accel(sph_context *c, float *density, float *pressure, float *accel3) {
+    REQUIRE(c, c && density && pressure && accel3, SPH_ERR_ARGUMENT, "sph_download_density_pressure_accel: NULL argument");
+    REQUIRE(c, c->s_valid && c->density_valid, SPH_ERR_STATE, "sph_download_density_pressure_accel: nothing computed yet");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const size_t n = c->n;
+    float *rho = c->d_tmp_f32, *prs = rho + n, *a3 = prs + n;
+    launch_scatter_dpa_by_id(c->pos_s, c->dp, c->acc, rho, prs, a3, (int)n, c->stream);
+    c->kernel_launches += 1;
+    CUDA_TRY(c, cudaMemcpyAsync(density, rho, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(pressure, prs, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(accel3, a3, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return check_launch(c, "download_density_pressure_accel");
+}
+
+int sph_download_neighbours(sph_context *c, int32_t *counts, int32_t *lists, uint64_t lists_capacity, uint64_t *total) {
+    REQUIRE(c, c && counts, SPH_ERR_ARGUMENT, "sph_download_neighbours: NULL argument");
+    REQUIRE(c, c->grid_valid && c->density_valid, SPH_ERR_STATE, "sph_download_neighbours: run sph_density_pressure first");
+    REQUIRE(c, c->opt_count_neighbours, SPH_ERR_STATE, "sph_download_neighbours: option count_neighbours is off");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const size_t n = c->n;
+    launch_scatter_by_id_i32(c->pos_s, c->nb_count, c->d_tmp_i32, (int)n, c->stream);
+    c->kernel_launches += 1;
+    CUDA_TRY(c, cudaMemcpyAsync(counts, c->d_tmp_i32, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    std::vector<long long> offsets(n + 1, 0);
+    for (size_t i = 0; i < n; ++i) offsets[i + 1] = offsets[i] + counts[i];
+    if (total) *total = (uint64_t)offsets[n];
+    if (!lists) return check_launch(c, "download_neighbours");
+    REQUIRE(c, lists_capacity >= (uint64_t)offsets[n], SPH_ERR_ARGUMENT, "sph_download_neighbours: lists buffer too small");
+    long long *d_off = nullptr;
+    int *d_lists = nullptr;
+    CUDA_TRY(c, dalloc(&d_off, n + 1));
+    cudaError_t e = dalloc(&d_lists, (size_t)offsets[n]);
+    if (e != cudaSuccess) {
+        cudaFree(d_off);
+        CUDA_TRY(c, e);
+    }
+    cudaMemcpyAsync(d_off, offsets.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream);
+    launch_neighbour_lists(c->pos_s, c->g.key_s, c->g.cell_start, d_off, d_lists, (int)n, c->P, c->stream);
+    c->kernel_launches += 1;
+    cudaMemcpyAsync(lists, d_lists, (size_t)offsets[n] * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_off);
+    cudaFree(d_lists);
+    CUDA_TRY(c, e);
+    for (size_t i = 0; i < n; ++i) std::sort(lists + offsets[i], lists + offsets[i + 1]);
+    return check_launch(c, "download_neighbours");
+}
+
+// ---------------------------------------------------------------- all-pairs variant
+static int brute_snapshot(sph_context *c) {
+    // S := A (no sort): the aux arrays are then aligned with the input order
+    if (!c->s_valid || c->a_aligned) {
+        CUDA_TRY(c, cudaMemcpyAsync(c->pos_s, c->pos_a, (size_t)c->n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->vel_s, c->vel_a, (size_t)c->n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+        c->s_valid = true;
+        c->grid_valid = false;
+        c->a_aligned = false;
+    }
+    return SPH_OK;
+}
+
+int sph_brute_density_pressure(sph_context *c, double *ms) {
+    REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = brute_snapshot(c);
+    if (rc) return rc;
+    PhaseTimer t(c, ms);
+    launch_brute_density(c->pos_s, c->dp, c->nb_count, (int)c->n, c->P, c->stream);
+    c->kernel_launches += 1;
+    c->density_valid = true;
+    c->forces_valid = false;
+    rc = check_launch(c, "brute_density_pressure");
+    return rc ? rc : t.finish();
+}
+
+int sph_brute_forces(sph_context *c, double *ms) {
+    REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    REQUIRE(c, c->s_valid && c->density_valid && !c->a_aligned, SPH_ERR_STATE, "sph_brute_forces: density first");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    PhaseTimer t(c, ms);
+    launch_brute_forces(c->pos_s, c->vel_s, c->dp, c->acc, (int)c->n, c->P, c->stream);
+    c->kernel_launches += 1;
+    c->forces_valid = true;
+    int rc = check_launch(c, "brute_forces");
+    return rc ? rc : t.finish();
+}
+
+int sph_brute_neighbour_counts(sph_context *c, int32_t *counts) {
+    REQUIRE(c, c && counts, SPH_ERR_ARGUMENT, "sph_brute_neighbour_counts: NULL argument");
+    REQUIRE(c, c->s_valid && c->density_valid, SPH_ERR_STATE, "sph_brute_neighbour_counts: density first");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    launch_scatter_by_id_i32(c->pos_s, c->nb_count, c->d_tmp_i32, (int)c->n, c->stream);
+    c->kernel_launches += 1;
+    CUDA_TRY(c, cudaMemcpyAsync(counts, c->d_tmp_i32, (size_t)c->n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return check_launch(c, "brute_neighbour_counts");
+}
+
+// ---------------------------------------------------------------- statistics
+int sph_stats(sph_context *c, double *out6) {
+    REQUIRE(c, c && out6, SPH_ERR_ARGUMENT, "sph_stats: NULL argument");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    launch_stats(view_pos(c), view_vel(c), (int)c->n, c->d_stats, c->stream);
+    c->kernel_launches += 1;
+    double h[8];
+    CUDA_TRY(c, cudaMemcpyAsync(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    const double n = (double)c->n;
+    unsigned bits;
+    std::memcpy(&bits, &h[5], sizeof(bits));
+    bits = (bits & 0x80000000u) ? (bits & 0x7fffffffu) : ~bits;
+    float ymax;
+    std::memcpy(&ymax, &bits, sizeof(ymax));
+    out6[0] = 0.5 * (double)c->P.mass * h[0];
+    out6[1] = n > 0 ? h[1] / n : 0;
+    out6[2] = n > 0 ? h[2] / n : 0;
+    out6[3] = n > 0 ? h[3] / n : 0;
+    out6[4] = n > 0 ? (double)ymax + (double)c->cfg.box[1] / 2.0 : 0;
+    out6[5] = n > 0 ? h[4] / n : 0;
+    return check_launch(c, "stats");
+}
+
+// ---------------------------------------------------------------- options / counters
+int sph_set_option(sph_context *c, const char *name, int value) {
+    REQUIRE(c, c && name, SPH_ERR_ARGUMENT, "sph_set_option: NULL argument");
+    const std::string k(name);
+    if (k == "density_variant") c->opt_density_variant = value;
+    else if (k == "forces_variant") c->opt_forces_variant = value;
+    else if (k == "use_graph") c->opt_use_graph = value;
+    else if (k == "count_neighbours") c->opt_count_neighbours = value;
+    else if (k == "flush_l2") { c->opt_flush_l2 = value; return SPH_OK; }
+    else return fail(c, SPH_ERR_ARGUMENT, "sph_set_option: unknown option " + k);
+    drop_graph(c);
+    return SPH_OK;
+}
+
+int sph_get_counter(const sph_context *c, const char *name, uint64_t *value) {
+    if (!c || !name || !value) return SPH_ERR_ARGUMENT;
+    const std::string k(name);
+    if (k == "kernel_launches") *value = c->kernel_launches;
+    else if (k == "graph_launches") *value = c->graph_launches;
+    else if (k == "steps") *value = c->steps;
+    else return SPH_ERR_ARGUMENT;
+    return SPH_OK;
+}
+
+int sph_comm_unique_id(uint8_t out[128]) {
+    (void)out;
+    return fail(nullptr, SPH_ERR_COMM, "sph_comm_unique_id: slab mode not built into this library yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,63 @@
+// sph_kernels.h — host-side launchers of the sm_100a kernels (internal to libsph_cuda.so).
+#pragma once
+
+#include "sph_device.cuh"
+
+namespace sph {
+
+constexpr int kScanTile = 2048;  // cells per scan tile (512 threads x int4)
+
+struct GridBuffers {
+    int *key_a;                       // [cap]   cell id in input order
+    int *off_a;                       // [cap]   arrival offset inside the cell (atomic)
+    int *bucket_src;                  // [cap]   input index per bucket slot
+    int *bucket_id;                   // [cap]   particle id per bucket slot
+    int *key_s;                       // [cap]   cell id in canonical order
+    int *count;                       // [cells_padded] per-cell histogram (zeroed by the scan)
+    int *cell_start;                  // [cells_padded] exclusive scan; [n_cells] = n
+    unsigned long long *scan_status;  // [tiles + 1]: tile look-back words, last = tile ticket
+    int n_scan_items;                 // n_cells + 1
+    int n_tiles;
+};
+
+// grid build: keys + histogram, exclusive scan, bucket, rank-by-id + SoA reorder
+void launch_cell_key_hist(const float4 *pos_a, int n, const GridBuffers &g, const Params &P, cudaStream_t st);
+void launch_scan(const GridBuffers &g, cudaStream_t st);
+void launch_bucket(const float4 *pos_a, int n, const GridBuffers &g, cudaStream_t st);
+void launch_rank_scatter(const float4 *pos_a, const float4 *vel_a, float4 *pos_s, float4 *vel_s, int n,
+                         const GridBuffers &g, cudaStream_t st);
+
+// neighbour passes on the canonical order
+void launch_density(const float4 *pos_s, const int *key_s, const int *cell_start, float4 *dp, int *nb_count, int n,
+                    const Params &P, int variant, cudaStream_t st);
+void launch_forces(const float4 *pos_s, const float4 *vel_s, const float4 *dp, const int *key_s, const int *cell_start,
+                   float4 *acc, int n, const Params &P, int variant, cudaStream_t st);
+void launch_integrate_collide(const float4 *pos_s, const float4 *vel_s, float4 *acc, float4 *pos_out, float4 *vel_out,
+                              int n, const Params &P, cudaStream_t st);
+
+// all-pairs validation kernels (CGPUBruteParticleSimulator semantics)
+void launch_brute_density(const float4 *pos, float4 *dp, int *nb_count, int n, const Params &P, cudaStream_t st);
+void launch_brute_forces(const float4 *pos, const float4 *vel, const float4 *dp, float4 *acc, int n, const Params &P,
+                         cudaStream_t st);
+
+// AoS <-> SoA at the boundary, taps
+struct ParticleAoS {  // == sph_particle
+    float position[4], velocity[4], acceleration[4];
+    int grid_position[4];
+    float density, pressure;
+    unsigned id, cell_id;
+};
+void launch_aos_to_soa(const ParticleAoS *aos, float4 *pos, float4 *vel, int n, cudaStream_t st);
+void launch_soa_to_aos(const float4 *pos, const float4 *vel, const float4 *acc, const float4 *dp, const int *key,
+                       ParticleAoS *aos_by_id, int id_base, int id_count, int n, const Params &P, cudaStream_t st);
+void launch_scatter_by_id_i32(const float4 *pos, const int *src, int *dst_by_id, int n, cudaStream_t st);
+void launch_scatter_dpa_by_id(const float4 *pos, const float4 *dp, const float4 *acc, float *rho, float *p, float *acc3,
+                              int n, cudaStream_t st);
+void launch_extract_ids(const float4 *pos, unsigned *ids, int n, cudaStream_t st);
+// neighbour lists: pass 1 counts (by id), pass 2 fills lists at offsets[id] (unsorted; host sorts each list)
+void launch_neighbour_lists(const float4 *pos_s, const int *key_s, const int *cell_start, const long long *offsets_by_id,
+                            int *lists, int n, const Params &P, cudaStream_t st);
+void launch_flush_l2(float4 *buf, size_t count, cudaStream_t st);
+void launch_stats(const float4 *pos, const float4 *vel, int n, double *out8, cudaStream_t st);
+
+}  // namespace sph

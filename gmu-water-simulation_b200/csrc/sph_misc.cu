@@ -1,0 +1,268 @@
+// sph_misc.cu — boundary conversions (80-byte AoS <-> SoA float4), validation taps, all-pairs
+// validation kernels and rollout statistics (sm_100a).
+#include "sph_kernels.h"
+
+namespace sph {
+
+// ================================================================= AoS <-> SoA
+// The reference's host mirror m_clParticles is an array of 80-byte CParticle::Physics records
+// (include/CParticle.h:19-43).  It is kept only at the boundary; on the device everything is SoA.
+__global__ void __launch_bounds__(256) k_aos_to_soa(const ParticleAoS *__restrict__ aos, float4 *__restrict__ pos,
+                                                    float4 *__restrict__ vel, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 *rec = reinterpret_cast<const float4 *>(aos + i);
+    float4 p = __ldg(rec + 0);
+    float4 v = __ldg(rec + 1);
+    const float4 tail = __ldg(rec + 4);  // density, pressure, id, cell_id
+    p.w = tail.z;                        // id bits ride in pos.w
+    v.w = 0.0f;
+    pos[i] = p;
+    vel[i] = v;
+}
+
+void launch_aos_to_soa(const ParticleAoS *aos, float4 *pos, float4 *vel, int n, cudaStream_t st) {
+    if (n <= 0) return;
+    k_aos_to_soa<<<(n + 255) / 256, 256, 0, st>>>(aos, pos, vel, n);
+}
+
+__global__ void __launch_bounds__(256) k_soa_to_aos(const float4 *__restrict__ pos, const float4 *__restrict__ vel,
+                                                    const float4 *__restrict__ acc, const float4 *__restrict__ dp,
+                                                    const int *__restrict__ key, ParticleAoS *__restrict__ out,
+                                                    int id_base, int id_count, int n,
+                                                    const __grid_constant__ Params P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = __ldg(pos + i);
+    const int id = __float_as_int(p.w);
+    const int slot = id - id_base;
+    if (slot < 0 || slot >= id_count) return;
+    const float4 v = __ldg(vel + i);
+    const float4 a = acc ? __ldg(acc + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 d = dp ? __ldg(dp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int k = key ? __ldg(key + i) : 0;
+    const int rxy = P.rx * P.ry;
+    const int cz = k / rxy, cy = (k - cz * rxy) / P.rx, cx = k - cz * rxy - cy * P.rx;
+    float4 *rec = reinterpret_cast<float4 *>(out + slot);
+    rec[0] = make_float4(p.x, p.y, p.z, 0.0f);
+    rec[1] = make_float4(v.x, v.y, v.z, 0.0f);
+    rec[2] = make_float4(a.x, a.y, a.z, 0.0f);
+    rec[3] = make_float4(__int_as_float(cx), __int_as_float(cy), __int_as_float(cz), 0.0f);
+    rec[4] = make_float4(d.x, d.y, p.w, __int_as_float(k));
+}
+
+void launch_soa_to_aos(const float4 *pos, const float4 *vel, const float4 *acc, const float4 *dp, const int *key,
+                       ParticleAoS *aos_by_id, int id_base, int id_count, int n, const Params &P, cudaStream_t st) {
+    if (n <= 0) return;
+    k_soa_to_aos<<<(n + 255) / 256, 256, 0, st>>>(pos, vel, acc, dp, key, aos_by_id, id_base, id_count, n, P);
+}
+
+// ================================================================= taps
+__global__ void __launch_bounds__(256) k_scatter_by_id_i32(const float4 *__restrict__ pos, const int *__restrict__ src,
+                                                           int *__restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dst[__float_as_int(__ldg(&pos[i].w))] = src[i];
+}
+void launch_scatter_by_id_i32(const float4 *pos, const int *src, int *dst_by_id, int n, cudaStream_t st) {
+    if (n <= 0) return;
+    k_scatter_by_id_i32<<<(n + 255) / 256, 256, 0, st>>>(pos, src, dst_by_id, n);
+}
+
+__global__ void __launch_bounds__(256) k_scatter_dpa(const float4 *__restrict__ pos, const float4 *__restrict__ dp,
+                                                     const float4 *__restrict__ acc, float *__restrict__ rho,
+                                                     float *__restrict__ prs, float *__restrict__ acc3, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int id = __float_as_int(__ldg(&pos[i].w));
+    const float4 d = __ldg(dp + i), a = __ldg(acc + i);
+    rho[id] = d.x;
+    prs[id] = d.y;
+    acc3[3 * (size_t)id + 0] = a.x;
+    acc3[3 * (size_t)id + 1] = a.y;
+    acc3[3 * (size_t)id + 2] = a.z;
+}
+void launch_scatter_dpa_by_id(const float4 *pos, const float4 *dp, const float4 *acc, float *rho, float *p, float *acc3,
+                              int n, cudaStream_t st) {
+    if (n <= 0) return;
+    k_scatter_dpa<<<(n + 255) / 256, 256, 0, st>>>(pos, dp, acc, rho, p, acc3, n);
+}
+
+__global__ void __launch_bounds__(256) k_extract_ids(const float4 *__restrict__ pos, unsigned *__restrict__ ids, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ids[i] = (unsigned)__float_as_int(__ldg(&pos[i].w));
+}
+void launch_extract_ids(const float4 *pos, unsigned *ids, int n, cudaStream_t st) {
+    if (n <= 0) return;
+    k_extract_ids<<<(n + 255) / 256, 256, 0, st>>>(pos, ids, n);
+}
+
+__global__ void __launch_bounds__(128) k_neighbour_lists(const float4 *__restrict__ pos, const int *__restrict__ key,
+                                                         const int *__restrict__ cell_start,
+                                                         const long long *__restrict__ offsets_by_id,
+                                                         int *__restrict__ lists, int n,
+                                                         const __grid_constant__ Params P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 pi = __ldg(pos + i);
+    long long w = offsets_by_id[__float_as_int(pi.w)];
+    const float h2 = P.h2;
+    for_each_row(__ldg(key + i), cell_start, P, [&](int a, int b) {
+        for (int j = a; j < b; ++j) {
+            const float4 pj = __ldg(pos + j);
+            const float r2 = r2_exact(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+            if (h2 - r2 >= 0.0f) lists[w++] = __float_as_int(pj.w);
+        }
+    });
+}
+void launch_neighbour_lists(const float4 *pos_s, const int *key_s, const int *cell_start, const long long *offsets_by_id,
+                            int *lists, int n, const Params &P, cudaStream_t st) {
+    if (n <= 0) return;
+    k_neighbour_lists<<<(n + 127) / 128, 128, 0, st>>>(pos_s, key_s, cell_start, offsets_by_id, lists, n, P);
+}
+
+// ================================================================= all-pairs validation kernels
+// CGPUBruteParticleSimulator semantics (resources/kernels/sph_brute.cl): every particle against every
+// particle, no grid.  Positions are staged through shared memory in tiles of BLOCK.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_brute_density(const float4 *__restrict__ pos, float4 *__restrict__ dp,
+                                                         int *__restrict__ nb_count, int n,
+                                                         const __grid_constant__ Params P) {
+    __shared__ float4 tile[BLOCK];
+    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    const float4 pi = i < n ? __ldg(pos + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float h2 = P.h2;
+    float sum = 0.0f;
+    int cnt = 0;
+    for (int base = 0; base < n; base += BLOCK) {
+        const int j = base + threadIdx.x;
+        tile[threadIdx.x] = j < n ? __ldg(pos + j) : make_float4(1e30f, 1e30f, 1e30f, 0.f);
+        __syncthreads();
+#pragma unroll 8
+        for (int t = 0; t < BLOCK; ++t) {
+            const float4 pj = tile[t];
+            const float r2 = r2_exact(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+            const float w = h2 - r2;
+            if (w >= 0.0f) {
+                ++cnt;
+                sum = fmaf(w * w, w, sum);
+            }
+        }
+        __syncthreads();
+    }
+    if (i >= n) return;
+    float rho = sum * P.poly6_f;
+    rho *= P.mass;
+    const float prs = P.gas_stiffness * (rho - P.rest_density);
+    const float inv_rho = 1.0f / rho;
+    dp[i] = make_float4(rho, prs, prs * inv_rho * inv_rho, inv_rho);
+    if (nb_count) nb_count[i] = cnt;
+}
+
+void launch_brute_density(const float4 *pos, float4 *dp, int *nb_count, int n, const Params &P, cudaStream_t st) {
+    if (n <= 0) return;
+    k_brute_density<256><<<(n + 255) / 256, 256, 0, st>>>(pos, dp, nb_count, n, P);
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_brute_forces(const float4 *__restrict__ pos, const float4 *__restrict__ vel,
+                                                        const float4 *__restrict__ dp, float4 *__restrict__ acc, int n,
+                                                        const __grid_constant__ Params P) {
+    __shared__ float4 tile[BLOCK];
+    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    const bool live = i < n;
+    const float4 pi = live ? __ldg(pos + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 vi = live ? __ldg(vel + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 di = live ? __ldg(dp + i) : make_float4(1.f, 0.f, 0.f, 1.f);
+    const float h2 = P.h2;
+    float fpx = 0.f, fpy = 0.f, fpz = 0.f, fvx = 0.f, fvy = 0.f, fvz = 0.f;
+    for (int base = 0; base < n; base += BLOCK) {
+        const int jj = base + threadIdx.x;
+        tile[threadIdx.x] = jj < n ? __ldg(pos + jj) : make_float4(1e30f, 1e30f, 1e30f, 0.f);
+        __syncthreads();
+        for (int t = 0; t < BLOCK; ++t) {
+            const float4 pj = tile[t];
+            const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+            const float r2 = r2_exact(dx, dy, dz);
+            const int j = base + t;
+            if (h2 - r2 >= 0.0f && j != i && live) {
+                const float4 vj = __ldg(vel + j), dj = __ldg(dp + j);
+                const float inv_r = rsqrtf(r2);
+                const float r = r2 * inv_r;
+                const float hr = P.h - r;
+                const float g = (P.spiky_f * hr) * (hr * inv_r) * (di.z + dj.z);
+                fpx = fmaf(g, dx, fpx);
+                fpy = fmaf(g, dy, fpy);
+                fpz = fmaf(g, dz, fpz);
+                const float l = (P.visc_f * hr) * dj.w;
+                fvx = fmaf(l, vj.x - vi.x, fvx);
+                fvy = fmaf(l, vj.y - vi.y, fvy);
+                fvz = fmaf(l, vj.z - vi.z, fvz);
+            }
+        }
+        __syncthreads();
+    }
+    if (!live) return;
+    const float rho = di.x;
+    const float sp = -P.mass * rho, sv = P.viscosity * P.mass;
+    acc[i] = make_float4((fpx * sp + fvx * sv + P.gx * rho) / rho, (fpy * sp + fvy * sv + P.gy * rho) / rho,
+                         (fpz * sp + fvz * sv + P.gz * rho) / rho, 0.0f);
+}
+
+void launch_brute_forces(const float4 *pos, const float4 *vel, const float4 *dp, float4 *acc, int n, const Params &P,
+                         cudaStream_t st) {
+    if (n <= 0) return;
+    k_brute_forces<256><<<(n + 255) / 256, 256, 0, st>>>(pos, vel, dp, acc, n, P);
+}
+
+// ================================================================= L2 eviction for benchmarking
+__global__ void __launch_bounds__(256) k_flush_l2(float4 *__restrict__ buf, size_t count) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+void launch_flush_l2(float4 *buf, size_t count, cudaStream_t st) { k_flush_l2<<<148 * 8, 256, 0, st>>>(buf, count); }
+
+// ================================================================= rollout statistics
+// out[0] = sum |v|^2, out[1..3] = sum pos, out[4] = sum |v|, out[5] = max y (as ordered-uint bits in out[5])
+__device__ __forceinline__ unsigned ordered_bits(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(256) k_stats(const float4 *__restrict__ pos, const float4 *__restrict__ vel, int n,
+                                               double *__restrict__ out) {
+    double s[5] = {0, 0, 0, 0, 0};
+    unsigned ymax = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = __ldg(pos + i), v = __ldg(vel + i);
+        const double v2 = (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z;
+        s[0] += v2;
+        s[1] += p.x;
+        s[2] += p.y;
+        s[3] += p.z;
+        s[4] += sqrt(v2);
+        ymax = max(ymax, ordered_bits(p.y));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) s[k] += __shfl_xor_sync(0xffffffffu, s[k], d);
+        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) atomicAdd(out + k, s[k]);
+        atomicMax(reinterpret_cast<unsigned *>(out + 5), ymax);
+    }
+}
+
+void launch_stats(const float4 *pos, const float4 *vel, int n, double *out8, cudaStream_t st) {
+    cudaMemsetAsync(out8, 0, 8 * sizeof(double), st);
+    if (n <= 0) return;
+    int blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_stats<<<blocks, 256, 0, st>>>(pos, vel, n, out8);
+}
+
+}  // namespace sph

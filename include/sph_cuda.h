@@ -1,0 +1,156 @@
+/*
+ * sph_cuda.h — C ABI of the B200-native SPH time step (libsph_cuda.so).
+ *
+ * This is the drop-in boundary.  It replaces the reference's device layer L1
+ * (CLWrapper + CLPlatforms) and device code L0 (the .cl files in resources/kernels) for ONE path:
+ * CBaseParticleSimulator::step() = updateGrid -> updateDensityPressure -> updateForces ->
+ * updateCollisions -> integrate (src/CBaseParticleSimulator.cpp:116-144).  The only caller is the
+ * C++ simulator CCUDAParticleSimulator (gmu-water-simulation_b200/core), which sits behind
+ * CBaseParticleSimulator exactly like CCPUParticleSimulator / CGPUParticleSimulator do.
+ *
+ * Conventions: plain C types only; every function returns an int status (SPH_OK == 0);
+ * sph_last_error() gives the message (≙ CLWrapper::getErrorMessage/checkError,
+ * include/CLWrapper.h:35-36).  Thread-compatible, not thread-safe (the reference is strictly
+ * single-threaded, src/CBaseParticleSimulator.cpp:35,76-81).  No OpenCL, no CPU fallback: when no
+ * CUDA device is usable every entry point fails with SPH_ERR_CUDA.
+ *
+ * Numerics follow the reference's CPU path (src/CCPUParticleSimulator.cpp): cell keys use fp64 math
+ * on fp32 positions, the neighbour predicate is the un-contracted fp32 (dx*dx+dy*dy)+dz*dz <= h*h,
+ * so keys, the canonical (cell,id) permutation and neighbour sets are bit-exact; density, pressure
+ * and acceleration are fp32 (rel 1e-5 vs. the mixed fp32/fp64 CPU path).
+ *
+ * All file:line citations are relative to the reference repository root.
+ */
+#ifndef SPH_CUDA_H
+#define SPH_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPH_ABI_VERSION 1
+
+enum sph_status {
+    SPH_OK = 0,
+    SPH_ERR_CUDA = 1,      /* a CUDA runtime call failed (≙ CLException, include/CLWrapper.h:18-22) */
+    SPH_ERR_ARGUMENT = 2,  /* bad argument / capacity exceeded */
+    SPH_ERR_STATE = 3,     /* call order violated (e.g. forces before the grid was built) */
+    SPH_ERR_COMM = 4       /* NCCL failure in slab mode */
+};
+
+/* CParticle::Physics / ParticleCL, byte for byte: 80 B, 16-aligned
+ * (include/CParticle.h:19-43, resources/kernels/sph_common.cl:29-39).  float3/int3 are 16 B. */
+typedef struct sph_particle {
+    float position[4];
+    float velocity[4];
+    float acceleration[4];
+    int32_t grid_position[4];
+    float density;
+    float pressure;
+    uint32_t id;
+    uint32_t cell_id;
+} sph_particle;
+
+/* sWall / WallCL: 32 B (include/CCollisionGeometry.h:23-30, resources/kernels/sph_common.cl:23-27) */
+typedef struct sph_wall {
+    float normal[4];
+    float position[4];
+} sph_wall;
+
+/* Everything the reference passes to its kernels as arguments or __constant data
+ * (CBaseParticleSimulator members include/CBaseParticleSimulator.h:80-90; constants
+ * include/CParticle.h:80-84, include/CCollisionGeometry.h:20-21). */
+typedef struct sph_config {
+    float box[3];            /* m_boxSize; the reference only builds cubes, a non-cubic box is the tank extension */
+    int32_t grid_res[3];     /* ceil(box/h), src/CBaseParticleSimulator.cpp:27-31 */
+    float h;                 /* CParticle::h */
+    float dt;                /* 0.01f, src/CBaseParticleSimulator.cpp:7 */
+    float mass;              /* CParticle::mass */
+    float viscosity;         /* CParticle::viscosity */
+    float gas_stiffness;     /* CParticle::gas_stiffness */
+    float rest_density;      /* CParticle::rest_density */
+    float gravity[3];        /* (0, GRAVITY_ACCELERATION, 0), include/CBaseParticleSimulator.h:19 */
+    float wall_k;            /* WALL_K */
+    float wall_damping;      /* WALL_DAMPING */
+    float wall_skin;         /* 0.01 "particle radius", src/CCollisionGeometry.cpp:124 */
+    int32_t wall_count;      /* 6 */
+    sph_wall walls[6];       /* left,bottom,back,right,top,front; include/CCollisionGeometry.h:79-120 */
+    uint32_t max_particles;  /* m_maxParticlesCount: device capacity */
+    int32_t device;          /* CUDA device ordinal (≙ the cl::Device ctor argument) */
+    /* slab decomposition along z (multi-GPU extension; world == 1 means single device) */
+    int32_t rank;
+    int32_t world;
+    uint8_t nccl_id[128];    /* ncclUniqueId from sph_comm_unique_id(), identical on all ranks */
+} sph_config;
+
+typedef struct sph_context sph_context;
+
+/* ---- enumeration (≙ CLPlatforms::getAllPlatforms/getDevices/getDeviceInfo, include/CLPlatforms.h:10-15) ---- */
+int sph_abi_version(void);
+int sph_device_count(int *count);
+int sph_device_name(int device, char *buf, size_t len);
+
+/* ---- lifetime (≙ CLWrapper ctor + createBuffer, include/CLWrapper.h:53,64) ---- */
+/* Fill cfg with the reference's constants, ceil(box/h) grid and the six +-box/2 walls. */
+int sph_config_init(sph_config *cfg, float box_x, float box_y, float box_z, uint32_t max_particles);
+int sph_create(const sph_config *cfg, sph_context **out);
+int sph_destroy(sph_context *ctx);
+const char *sph_last_error(const sph_context *ctx); /* ctx may be NULL: error of the last failed create/enumeration */
+
+/* ---- state (≙ enqueueWrite/enqueueRead, include/CLWrapper.h:66-67) ---- */
+/* Replace the device state with n particles from the 80-byte AoS host mirror (m_clParticles). */
+int sph_upload_particles(sph_context *ctx, const sph_particle *aos, uint32_t n);
+/* Fountain emission (src/CBaseParticleSimulator.cpp:187-210): append n_new particles. */
+int sph_append_particles(sph_context *ctx, const sph_particle *aos, uint32_t n_new);
+/* Read back on demand into aos[id] (the host mirror is indexed by id); capacity in records. */
+int sph_download_particles(sph_context *ctx, sph_particle *aos, uint32_t capacity, uint32_t *n_out);
+int sph_particle_count(const sph_context *ctx, uint32_t *n_out);
+/* ≙ CGPUBaseParticleSimulator::setGravityVector, src/CGPUBaseParticleSimulator.cpp:11-15 */
+int sph_set_gravity(sph_context *ctx, float gx, float gy, float gz);
+/* Page-lock the caller's host mirror once (m_clParticles is reserved up front, src/CBaseParticleSimulator.cpp:42)
+ * so per-step uploads/downloads run at full PCIe speed; unpinned again by sph_destroy. */
+int sph_pin_host_buffer(sph_context *ctx, void *ptr, size_t bytes);
+
+/* ---- the five phases (≙ the enqueueKernel call sites); *ms (may be NULL) receives the device time
+ * in milliseconds (≙ CLWrapper::getEventDuration, include/CLWrapper.h:50).  With ms == NULL the call
+ * is asynchronous on the context's stream. ---- */
+int sph_update_grid(sph_context *ctx, double *ms);       /* keys -> counting sort -> SoA reorder; ≙ src/CGPUParticleSimulator.cpp:57-139 */
+int sph_density_pressure(sph_context *ctx, double *ms);  /* ≙ src/CGPUParticleSimulator.cpp:141-155 */
+int sph_forces(sph_context *ctx, double *ms);            /* pressure + viscosity + gravity; ≙ src/CGPUParticleSimulator.cpp:157-173 */
+int sph_collisions(sph_context *ctx, double *ms);        /* no-op: walls are fused into integrate (CPU path: src/CCPUParticleSimulator.cpp:205-209) */
+int sph_integrate(sph_context *ctx, double *ms);         /* wall penalty force + integration fused; ≙ src/CGPUBaseParticleSimulator.cpp:59-97 */
+/* n_steps full steps back to back on the device (CUDA graph), no host transfer; *ms = total device time. */
+int sph_step(sph_context *ctx, int n_steps, double *ms);
+int sph_synchronize(sph_context *ctx);
+
+/* ---- validation taps (all arrays indexed by particle id unless stated) ---- */
+int sph_download_keys(sph_context *ctx, int32_t *keys);                /* cell id of each particle as of the last update_grid */
+int sph_download_permutation(sph_context *ctx, uint32_t *sorted_ids);  /* ids in canonical (cell_id, id) order */
+int sph_download_cell_start(sph_context *ctx, int32_t *cell_start);    /* cells+1 entries */
+int sph_download_density_pressure_accel(sph_context *ctx, float *density, float *pressure, float *accel3);
+/* neighbour sets of the grid walk (r2 <= h2, self included): counts[n]; lists (may be NULL) receives the
+ * concatenated ascending id lists, particle 0 first; *total = sum(counts) */
+int sph_download_neighbours(sph_context *ctx, int32_t *counts, int32_t *lists, uint64_t lists_capacity, uint64_t *total);
+
+/* ---- all-pairs variant (CGPUBruteParticleSimulator semantics, resources/kernels/sph_brute.cl) ---- */
+int sph_brute_density_pressure(sph_context *ctx, double *ms);
+int sph_brute_forces(sph_context *ctx, double *ms);
+int sph_brute_neighbour_counts(sph_context *ctx, int32_t *counts);
+
+/* ---- rollout statistics on the device: out[0]=KE, out[1..3]=COM, out[4]=max(y)+b/2, out[5]=mean speed ---- */
+int sph_stats(sph_context *ctx, double *out6);
+
+/* ---- tuning / introspection ---- */
+int sph_set_option(sph_context *ctx, const char *name, int value);
+int sph_get_counter(const sph_context *ctx, const char *name, uint64_t *value); /* "kernel_launches", "graph_launches", "steps" */
+
+/* ---- slab mode plumbing: rank 0 creates the id, the launcher broadcasts it (torch.distributed / file) ---- */
+int sph_comm_unique_id(uint8_t out[128]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPH_CUDA_H */

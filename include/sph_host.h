@@ -1,0 +1,49 @@
+/*
+ * sph_host.h — C facade of the C++ simulator objects (libsph_host.so), for non-C++ drivers
+ * (tests, bench.py).  The reference-facing boundary is include/sph_cuda.h; this header only lets a
+ * Python process construct and drive the same CCUDAParticleSimulator a C++ caller would, the way
+ * MainWindow does (src/mainwindow.cpp:171-201,243-287).
+ */
+#ifndef SPH_HOST_H
+#define SPH_HOST_H
+
+#include <stdint.h>
+
+#include "sph_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gmu_sim gmu_sim;
+
+/* type: "cuda" (uniform grid), "cuda_brute" (all pairs), "scene_only" (no device; scene generation and
+ * emission only).  scenario: 0 = DAM_BREAK, 1 = FOUNTAIN (include/CBaseParticleSimulator.h:21-25). */
+gmu_sim *gmu_sim_create(const char *type, float box_x, float box_y, float box_z, int device, int scenario);
+void gmu_sim_destroy(gmu_sim *s);
+const char *gmu_sim_last_error(void);
+
+int gmu_sim_setup_scene(gmu_sim *s);                               /* setupScene() */
+int gmu_sim_step(gmu_sim *s, int n);                               /* n timer ticks: doWork() = step() + counters */
+int gmu_sim_step_many(gmu_sim *s, int n, double *device_ms);       /* fused device steps (extension) */
+int gmu_sim_emit(gmu_sim *s, int n_steps);                         /* scene_only: run the emitter n steps */
+int gmu_sim_set_mirror_mode(gmu_sim *s, int mode);                 /* 0 resident, 1 download, 2 round trip per step */
+int gmu_sim_sync_host(gmu_sim *s);                                 /* device -> host mirror */
+int gmu_sim_set_gravity(gmu_sim *s, float gx, float gy, float gz); /* setGravityVector */
+int gmu_sim_key(gmu_sim *s, int qt_key);                           /* onKeyPressed */
+int gmu_sim_set_profiling(gmu_sim *s, int on, int stride);
+int gmu_sim_set_emission_multiplier(gmu_sim *s, int nozzles);
+uint64_t gmu_sim_particle_count(gmu_sim *s);
+uint64_t gmu_sim_max_particle_count(gmu_sim *s);
+uint64_t gmu_sim_iteration(gmu_sim *s);
+const sph_particle *gmu_sim_host_particles(gmu_sim *s);            /* m_clParticles.data() */
+sph_context *gmu_sim_context(gmu_sim *s);                          /* the simulator's device context (taps) */
+const char *gmu_sim_device_name(gmu_sim *s);                       /* getSelectedDevice() */
+uint64_t gmu_sim_event_count(gmu_sim *s);
+uint64_t gmu_sim_get_events(gmu_sim *s, double *out7, uint64_t max_events);
+int gmu_sim_export_logs(gmu_sim *s, const char *dir, const char *sim_name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPH_HOST_H */

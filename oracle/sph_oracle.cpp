@@ -73,7 +73,7 @@ struct OracleSim {
     int res[3];
     int64_t max_count = 0;
     // per particle (index == id, as in m_clParticles / CParticle)
-    std::vector<V3> pos, vel, acc, acc_sph;
+    std::vector<V3> pos, vel, acc, acc_sph, acc_wall;
     std::vector<float> density, pressure, acc_scale;
     // CGrid: one vector of particle ids per cell (include/CGrid.h:24-28, src/CGrid.cpp:17-18)
     std::vector<std::vector<int32_t>> cells;
@@ -154,6 +154,7 @@ void oracle_add_particle(OracleSim *s, float x, float y, float z, float vx, floa
     s->vel.emplace_back(vx, vy, vz);
     s->acc.emplace_back(0.0f, 0.0f, 0.0f);
     s->acc_sph.emplace_back(0.0f, 0.0f, 0.0f);
+    s->acc_wall.emplace_back(0.0f, 0.0f, 0.0f);
     s->acc_scale.push_back(0.0f);
     s->density.push_back(0.0f);
     s->pressure.push_back(0.0f);
@@ -186,7 +187,7 @@ void oracle_setup_scene(OracleSim *s) {
 
 void oracle_set_state(OracleSim *s, int64_t n, const float *pos, const float *vel) {
     for (auto &c : s->cells) c.clear();
-    s->pos.clear(); s->vel.clear(); s->acc.clear(); s->acc_sph.clear();
+    s->pos.clear(); s->vel.clear(); s->acc.clear(); s->acc_sph.clear(); s->acc_wall.clear();
     s->acc_scale.clear(); s->density.clear(); s->pressure.clear();
     for (int64_t i = 0; i < n; ++i)
         oracle_add_particle(s, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]);
@@ -318,7 +319,9 @@ static inline void force_finish(OracleSim *s, int32_t i, ForceAcc &fa) {
     s->acc_sph[i] = a;
     double scale = ((double)kMass * rho * fa.mag_p + (double)(kViscosity * kMass) * fa.mag_v +
                     std::sqrt((double)length_squared(f_gravity))) / (double)rho;
-    a += s->wall_bounce(s->pos[i], s->vel[i], &scale);
+    const V3 wall = s->wall_bounce(s->pos[i], s->vel[i], &scale);
+    s->acc_wall[i] = wall;
+    a += wall;
     s->acc[i] = a;
     s->acc_scale[i] = (float)scale;
 }
@@ -400,6 +403,7 @@ void oracle_get_pos(const OracleSim *s, float *o) { copy3(s->pos, o); }
 void oracle_get_vel(const OracleSim *s, float *o) { copy3(s->vel, o); }
 void oracle_get_acc(const OracleSim *s, float *o) { copy3(s->acc, o); }
 void oracle_get_acc_sph(const OracleSim *s, float *o) { copy3(s->acc_sph, o); }
+void oracle_get_acc_wall(const OracleSim *s, float *o) { copy3(s->acc_wall, o); }
 void oracle_get_acc_scale(const OracleSim *s, float *o) { std::memcpy(o, s->acc_scale.data(), s->acc_scale.size() * sizeof(float)); }
 void oracle_get_density(const OracleSim *s, float *o) { std::memcpy(o, s->density.data(), s->density.size() * sizeof(float)); }
 void oracle_get_pressure(const OracleSim *s, float *o) { std::memcpy(o, s->pressure.data(), s->pressure.size() * sizeof(float)); }

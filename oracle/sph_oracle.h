@@ -68,6 +68,7 @@ void oracle_get_pos(const OracleSim *s, float *out3n);
 void oracle_get_vel(const OracleSim *s, float *out3n);
 void oracle_get_acc(const OracleSim *s, float *out3n);       /* SPH + wall term (what updateForces leaves) */
 void oracle_get_acc_sph(const OracleSim *s, float *out3n);   /* before the wall term is added */
+void oracle_get_acc_wall(const OracleSim *s, float *out3n);  /* the wall term alone (inverseBoundingBoxBounce) */
 void oracle_get_acc_scale(const OracleSim *s, float *outn);  /* sum of |terms| / rho: conditioning scale for tolerances */
 void oracle_get_density(const OracleSim *s, float *outn);
 void oracle_get_pressure(const OracleSim *s, float *outn);

@@ -50,6 +50,7 @@ def _load():
         "oracle_get_vel": (None, [vp, vp]),
         "oracle_get_acc": (None, [vp, vp]),
         "oracle_get_acc_sph": (None, [vp, vp]),
+        "oracle_get_acc_wall": (None, [vp, vp]),
         "oracle_get_acc_scale": (None, [vp, vp]),
         "oracle_get_density": (None, [vp, vp]),
         "oracle_get_pressure": (None, [vp, vp]),
@@ -174,6 +175,7 @@ class Oracle:
     vel = property(lambda self: self._vec("oracle_get_vel", 3))
     acc = property(lambda self: self._vec("oracle_get_acc", 3))
     acc_sph = property(lambda self: self._vec("oracle_get_acc_sph", 3))
+    acc_wall = property(lambda self: self._vec("oracle_get_acc_wall", 3))
     acc_scale = property(lambda self: self._vec("oracle_get_acc_scale", 1))
     density = property(lambda self: self._vec("oracle_get_density", 1))
     pressure = property(lambda self: self._vec("oracle_get_pressure", 1))

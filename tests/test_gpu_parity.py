@@ -1,0 +1,304 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): cell keys, canonical permutation, cell ranges and neighbour sets are
+bit-exact; density, pressure, acceleration within rel 1e-5 in fp32 (pressure with the absolute floor
+k*rho because p = k (rho - rho0) cancels; acceleration relative to max(|a|, sum of |terms|)); the
+integrator is bit-exact given the device's own acceleration.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle_binding import DAM_BREAK, FOUNTAIN, Oracle
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def state_after(box, steps, scenario=DAM_BREAK):
+    o = Oracle(box, scenario).setup_scene()
+    if steps:
+        o.step(steps)
+    return o
+
+
+def make_ctx(gws, box, pos, vel, cap=None):
+    ctx = gws.SphContext(box, cap or max(len(pos), 1))
+    ctx.upload(gws.particles_from_arrays(pos, vel))
+    return ctx
+
+
+def check_density(o, rho, prs):
+    assert np.all(np.abs(rho - o.density) <= RTOL * np.abs(o.density)), np.abs(rho / o.density - 1).max()
+    floor = np.maximum(np.abs(o.pressure), 3.0 * o.density)
+    assert np.all(np.abs(prs - o.pressure) <= RTOL * floor)
+
+
+def check_acc(ref, scale, got):
+    tol = RTOL * np.maximum(np.linalg.norm(ref, axis=1), scale)
+    err = np.abs(got - ref).max(axis=1)
+    assert np.all(err <= tol), f"worst acc error/tol = {(err / tol).max():.3f}"
+
+
+def phase_parity(gws, o, box):
+    """One step of both implementations from the oracle's current state, checked phase by phase."""
+    pos, vel = o.pos, o.vel
+    ctx = make_ctx(gws, box, pos, vel)
+    # ---- grid
+    o.update_grid()
+    ctx.update_grid()
+    assert np.array_equal(ctx.keys(), o.keys())
+    cs, ids = o.cells()
+    assert np.array_equal(ctx.cell_start(), cs)
+    assert np.array_equal(ctx.permutation().astype(np.int32), ids)
+    # ---- density / pressure / neighbour sets
+    o.update_density_pressure()
+    ctx.density_pressure()
+    rho, prs, _ = ctx.density_pressure_accel()
+    check_density(o, rho, prs)
+    oc, ol = o.neighbours()
+    gc, gl = ctx.neighbours()
+    assert np.array_equal(gc, oc)
+    assert np.array_equal(gl, ol)
+    # ---- forces (SPH part), then walls + integration
+    o.update_forces()
+    ctx.forces()
+    _, _, acc_sph = ctx.density_pressure_accel()
+    check_acc(o.acc_sph, o.acc_scale, acc_sph)
+    ctx.collisions()
+    ctx.integrate()
+    _, _, acc_tot = ctx.density_pressure_accel()
+    # wall term is computed from identical pos/vel: total == fl32(sph_gpu + wall_oracle) bit for bit
+    assert np.array_equal((acc_sph + o.acc_wall).view(np.uint32), acc_tot.view(np.uint32))
+    check_acc(o.acc, o.acc_scale, acc_tot)
+    # integrator: bit-exact given the device's own acceleration (src/CCPUParticleSimulator.cpp:220-221)
+    dt = np.float32(0.01)
+    new_pos = (pos + vel * dt) + (acc_tot * dt) * dt
+    new_vel = (new_pos - pos) / dt
+    rec = ctx.download()
+    assert np.array_equal(rec["id"], np.arange(o.n, dtype=np.uint32))
+    assert np.array_equal(rec["position"][:, :3].view(np.uint32), new_pos.view(np.uint32))
+    assert np.array_equal(rec["velocity"][:, :3].view(np.uint32), new_vel.view(np.uint32))
+    # and against the oracle's own integration within the acceleration tolerance
+    o.integrate()
+    assert np.abs(rec["position"][:, :3] - o.pos).max() <= 1e-4 * 0.0457
+    # the record also carries this step's density/pressure/cell id, like the reference's read-back
+    assert np.array_equal(rec["cell_id"].astype(np.int32), ctx.keys())
+    assert np.array_equal(rec["density"], rho)
+    ctx.close()
+
+
+@pytest.mark.parametrize("box,steps", [(0.4, 0), (0.4, 1), (0.4, 10), (0.4, 100), (0.9, 0), (0.9, 25)])
+def test_phase_parity_dam_break(gws, box, steps):
+    phase_parity(gws, state_after(box, steps), box)
+
+
+def test_phase_parity_non_cubic_box(gws):
+    box = (0.5, 0.3, 0.7)
+    phase_parity(gws, state_after(box, 12), box)
+
+
+def test_phase_parity_golden_fixture(gws):
+    """Inputs and expected outputs from the committed fixture (no oracle run involved)."""
+    g = np.load(os.path.join(GOLDEN, "oracle_phase_0p4_step10.npz"))
+    ctx = make_ctx(gws, 0.4, g["pos"], g["vel"])
+    ctx.update_grid()
+    ctx.density_pressure()
+    ctx.forces()
+    assert np.array_equal(ctx.keys(), g["keys"])
+    assert np.array_equal(ctx.cell_start(), g["cell_start"])
+    assert np.array_equal(ctx.permutation().astype(np.int32), g["perm"])
+    counts, _ = ctx.neighbours(lists=False)
+    assert np.array_equal(counts, g["nb_counts"])
+    rho, prs, acc = ctx.density_pressure_accel()
+    assert np.all(np.abs(rho - g["density"]) <= RTOL * g["density"])
+    check_acc(g["acc_sph"], g["acc_scale"], acc)
+
+
+def test_rollout_with_resync(gws):
+    """Per-step parity along a trajectory: every 10th step of 60 restart the device from the oracle state."""
+    box = 0.4
+    o = Oracle(box).setup_scene()
+    for _ in range(6):
+        ctx = make_ctx(gws, box, o.pos, o.vel)
+        o.step(1)
+        ctx.step(1)
+        rec = ctx.download()
+        assert np.abs(rec["position"][:, :3] - o.pos).max() <= 1e-4 * 0.0457
+        o.step(9)
+        ctx.close()
+
+
+def test_fused_step_equals_phase_path_bitwise(gws):
+    o = state_after(0.4, 5)
+    a = make_ctx(gws, 0.4, o.pos, o.vel)
+    b = make_ctx(gws, 0.4, o.pos, o.vel)
+    for _ in range(4):
+        a.update_grid(); a.density_pressure(); a.forces(); a.collisions(); a.integrate()
+    b.step(1)          # direct launches
+    b.step(3)          # CUDA graph
+    ra, rb = a.download(), b.download()
+    for f in ("position", "velocity", "acceleration", "density", "pressure", "cell_id"):
+        assert np.array_equal(ra[f].view(np.uint32), rb[f].view(np.uint32)), f
+    assert b.counter("graph_launches") == 3
+
+
+def test_determinism_and_input_order_independence(gws):
+    """The canonical (cell,id) order makes results a pure function of the state: shuffling the upload
+    order or re-running gives bit-identical outputs."""
+    o = state_after(0.4, 7)
+    pos, vel = o.pos, o.vel
+    n = len(pos)
+    a = make_ctx(gws, 0.4, pos, vel)
+    rng = np.random.default_rng(0xC0FFEE)
+    perm = rng.permutation(n)
+    b = gws.SphContext(0.4, n)
+    b.upload(gws.particles_from_arrays(pos[perm], vel[perm], ids=perm))
+    a.step(5); b.step(5)
+    ra, rb = a.download(), b.download()
+    assert np.array_equal(ra["position"].view(np.uint32), rb["position"].view(np.uint32))
+    assert np.array_equal(ra["density"].view(np.uint32), rb["density"].view(np.uint32))
+
+
+def test_brute_force_config(gws):
+    """config 2: all-pairs semantics at 32.5K particles; neighbour sets equal the grid walk and the oracle."""
+    box = 1.14
+    o = state_after(box, 3)
+    assert o.n == 32500
+    pos, vel = o.pos, o.vel
+    ctx = make_ctx(gws, box, pos, vel)
+    ctx.brute_density_pressure()
+    brute_counts = ctx.brute_neighbour_counts()
+    rho_b, prs_b, _ = ctx.density_pressure_accel()
+    ctx.brute_forces()
+    _, _, acc_b = ctx.density_pressure_accel()
+    ctx.integrate()
+    rec_b = ctx.download()
+    ctx.upload(gws.particles_from_arrays(pos, vel))
+    ctx.update_grid(); ctx.density_pressure()
+    grid_counts, _ = ctx.neighbours(lists=False)
+    o.update_grid(); o.update_density_pressure(); o.update_forces()
+    oc, _ = o.neighbours(lists=False)
+    assert np.array_equal(brute_counts, grid_counts)
+    assert np.array_equal(brute_counts, oc)
+    check_density(o, rho_b, prs_b)
+    check_acc(o.acc_sph, o.acc_scale, acc_b)
+    o.integrate()
+    assert np.abs(rec_b["position"][:, :3] - o.pos).max() <= 1e-4 * 0.0457
+
+
+def test_fountain_through_simulator(gws):
+    """Fountain scene driven through CCUDAParticleSimulator (emission on the host, append on the device)."""
+    box = 0.4
+    sim = gws.Simulator("cuda", box, scenario=gws.FOUNTAIN).setup_scene()
+    o = Oracle(box, FOUNTAIN).setup_scene()
+    steps = 40
+    sim.step(steps)
+    o.step(steps)
+    sim.sync_host()
+    hp = sim.host_particles()
+    assert sim.n == o.n == 7 * steps
+    assert np.abs(hp["position"][:, :3] - o.pos).max() <= 2e-4 * 0.0457
+    assert np.abs(hp["velocity"][:, :3] - o.vel).max() <= 1e-3
+
+
+def test_simulator_phase_path_and_mirror_modes(gws):
+    box = 0.4
+    o = Oracle(box).setup_scene()
+    sim = gws.Simulator("cuda", box).setup_scene()
+    assert "B200" in sim.device or "NVIDIA" in sim.device
+    sim.set_profiling(True, 1)
+    sim.set_mirror_mode(2)  # upload + download every step (the reference OpenCL path's semantics)
+    sim.step(3)
+    o.step(3)
+    hp = sim.host_particles()
+    assert np.abs(hp["position"][:, :3] - o.pos).max() <= 1e-4 * 0.0457
+    ev = sim.events()
+    assert ev.shape == (3, 7) and np.all(ev[:, 2:5] > 0) and np.all(ev[:, 5] == 0)
+    # resident fused path continues from the same state
+    sim.set_mirror_mode(0)
+    sim.step_many(7)
+    o.step(7)
+    sim.sync_host()
+    assert np.abs(sim.host_particles()["position"][:, :3] - o.pos).max() <= 2e-4 * 0.0457
+    assert sim.iteration == 10
+
+
+def test_gravity_vector(gws):
+    o = state_after(0.4, 2)
+    ctx = make_ctx(gws, 0.4, o.pos, o.vel)
+    g = (-1.0, -9.80665, 0.5)
+    o.set_gravity(g); ctx.set_gravity(g)
+    o.update_grid(); o.update_density_pressure(); o.update_forces()
+    ctx.update_grid(); ctx.density_pressure(); ctx.forces()
+    check_acc(o.acc_sph, o.acc_scale, ctx.density_pressure_accel()[2])
+
+
+def test_edge_cases(gws):
+    # empty state, single particle, particles outside the box (clamped keys), capacity and call-order errors
+    ctx = gws.SphContext(0.4, 16)
+    ctx.upload(gws.particles_from_arrays(np.zeros((0, 3))))
+    assert ctx.step(2) == 0.0 and ctx.n == 0
+    with pytest.raises(gws.SphError):
+        ctx.upload(gws.particles_from_arrays(np.zeros((17, 3))))
+    pos = np.array([[0, 0, 0], [5.0, -5.0, 0.1], [-0.2, -0.2, -0.2], [0.19999, 0.2, 0.25]], dtype=np.float32)
+    ctx.upload(gws.particles_from_arrays(pos))
+    with pytest.raises(gws.SphError):
+        ctx.forces()
+    o = Oracle(0.4).set_state(pos)
+    o.update_grid(); ctx.update_grid()
+    assert np.array_equal(ctx.keys(), o.keys())
+    o.update_density_pressure(); ctx.density_pressure()
+    rho, prs, _ = ctx.density_pressure_accel()
+    check_density(o, rho, prs)
+    assert abs(rho[0] - 328.2934) < 1e-3
+    ctx.append(gws.particles_from_arrays(np.array([[0.01, 0.0, 0.0]], dtype=np.float32), ids=[4]))
+    assert ctx.n == 5
+    ctx.step(1)
+    assert np.array_equal(np.sort(ctx.permutation()), np.arange(5))
+
+
+def test_dense_cell_overflow_path(gws):
+    """More neighbours than the force kernel's hit queue holds (very dense clump): overflow path."""
+    rng = np.random.default_rng(1234)
+    pos = (rng.random((400, 3), dtype=np.float32) - 0.5) * np.float32(0.03)
+    o = Oracle(0.4).set_state(pos)
+    ctx = make_ctx(gws, 0.4, pos, np.zeros_like(pos))
+    o.update_grid(); o.update_density_pressure(); o.update_forces()
+    ctx.update_grid(); ctx.density_pressure(); ctx.forces()
+    oc, ol = o.neighbours(); gc, gl = ctx.neighbours()
+    assert oc.max() > 100 and np.array_equal(gc, oc) and np.array_equal(gl, ol)
+    rho, prs, acc = ctx.density_pressure_accel()
+    check_density(o, rho, prs)
+    check_acc(o.acc_sph, o.acc_scale, acc)
+
+
+def test_full_size_properties_1m(gws):
+    """BASELINE config 3 (1,011,240 particles): size-independent properties instead of an oracle run."""
+    box = 3.62
+    sim = gws.Simulator("cuda", box).setup_scene()
+    n = sim.n
+    assert n == 1011240
+    ctx = sim.context()
+    sim.step_many(20)
+    ctx.update_grid()
+    keys, perm, cs = ctx.keys(), ctx.permutation(), ctx.cell_start()
+    assert np.array_equal(np.sort(perm), np.arange(n, dtype=np.uint32))          # a permutation
+    assert np.array_equal(np.diff(cs), np.bincount(keys, minlength=ctx.n_cells))  # ranges == histogram
+    assert cs[0] == 0 and cs[-1] == n
+    sk = keys[perm]
+    assert np.all(np.diff(sk) >= 0)                                               # sorted by cell
+    same = np.diff(sk) == 0
+    assert np.all(np.diff(perm.astype(np.int64))[same] > 0)                       # ids ascend inside a cell
+    ctx.density_pressure()
+    rho, _, _ = ctx.density_pressure_accel()
+    counts, _ = ctx.neighbours(lists=False)
+    assert rho.min() >= 328.29 and counts.min() >= 1 and np.isfinite(rho).all()
+    st = ctx.stats()
+    assert np.isfinite(st["ke"]) and st["fill"] <= box * 1.01
+    # keys agree with the oracle's key formula on the downloaded positions (fp64 math on the host)
+    ctx.forces(); ctx.integrate()
+    rec = ctx.download()
+    assert np.isfinite(rec["position"]).all()
