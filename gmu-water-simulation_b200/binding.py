@@ -49,9 +49,9 @@ class SphConfig(C.Structure):
         ("gas_stiffness", C.c_float),
         ("rest_density", C.c_float),
         ("gravity", C.c_float * 3),
-        ("wall_k", C.c_float),
-        ("wall_damping", C.c_float),
-        ("wall_skin", C.c_float),
+        ("wall_k", C.c_double),
+        ("wall_damping", C.c_double),
+        ("wall_skin", C.c_double),
         ("wall_count", C.c_int32),
         ("walls", _Wall * 6),
         ("max_particles", C.c_uint32),

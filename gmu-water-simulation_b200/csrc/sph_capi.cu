@@ -112,9 +112,9 @@ Params make_params(const sph_config &c) {
     P.gx = c.gravity[0];
     P.gy = c.gravity[1];
     P.gz = c.gravity[2];
-    P.wall_k_f = c.wall_k;
-    P.wall_damping_d = (double)c.wall_damping;
-    P.wall_skin_d = (double)c.wall_skin;
+    P.wall_k_f = (float)c.wall_k;  // narrowed where it meets a QVector3D (float overloads only)
+    P.wall_damping_d = c.wall_damping;
+    P.wall_skin_d = c.wall_skin;
     P.wall_count = c.wall_count;
     for (int w = 0; w < 6; ++w) {
         P.walls[w] = {c.walls[w].normal[0],   c.walls[w].normal[1],   c.walls[w].normal[2],
@@ -226,9 +226,9 @@ int sph_config_init(sph_config *cfg, float bx, float by, float bz, uint32_t max_
     cfg->dt = 0.01f;              // src/CBaseParticleSimulator.cpp:7
     for (int a = 0; a < 3; ++a) cfg->grid_res[a] = (int)std::ceil(cfg->box[a] / cfg->h);  // :27-31 (float division)
     cfg->gravity[1] = -9.80665f;  // include/CBaseParticleSimulator.h:19
-    cfg->wall_k = 10000.0f;       // include/CCollisionGeometry.h:20
-    cfg->wall_damping = -0.9f;    // :21 (exact value used: the double -0.9, see Params)
-    cfg->wall_skin = 0.01f;
+    cfg->wall_k = 10000.0;        // include/CCollisionGeometry.h:20
+    cfg->wall_damping = -0.9;     // :21
+    cfg->wall_skin = 0.01;
     cfg->wall_count = 6;
     const float mn[3] = {-(bx / 2.0f), -(by / 2.0f), -(bz / 2.0f)}, mx[3] = {bx / 2.0f, by / 2.0f, bz / 2.0f};
     for (int a = 0; a < 3; ++a) {  // include/CCollisionGeometry.h:79-120

@@ -73,9 +73,9 @@ typedef struct sph_config {
     float gas_stiffness;     /* CParticle::gas_stiffness */
     float rest_density;      /* CParticle::rest_density */
     float gravity[3];        /* (0, GRAVITY_ACCELERATION, 0), include/CBaseParticleSimulator.h:19 */
-    float wall_k;            /* WALL_K */
-    float wall_damping;      /* WALL_DAMPING */
-    float wall_skin;         /* 0.01 "particle radius", src/CCollisionGeometry.cpp:124 */
+    double wall_k;           /* WALL_K 10000.0 — the reference's macros are double literals and enter the */
+    double wall_damping;     /* WALL_DAMPING (-0.9)   arithmetic as doubles (src/CCollisionGeometry.cpp:124-128) */
+    double wall_skin;        /* 0.01 "particle radius", src/CCollisionGeometry.cpp:124 */
     int32_t wall_count;      /* 6 */
     sph_wall walls[6];       /* left,bottom,back,right,top,front; include/CCollisionGeometry.h:79-120 */
     uint32_t max_particles;  /* m_maxParticlesCount: device capacity */
