@@ -188,10 +188,8 @@ def run_ours(args):
     sim = gws.Simulator("cuda", box, device=local).setup_scene()
     ctx = sim.context()
     n = sim.n
-    if args.density_variant is not None:
-        ctx.set_option("density_variant", args.density_variant)
-    if args.forces_variant is not None:
-        ctx.set_option("forces_variant", args.forces_variant)
+    if args.neighbour_variant is not None:
+        ctx.set_option("neighbour_variant", args.neighbour_variant)
 
     # ---- pre-roll so the dam has collapsed and the state is irregular, then warm-up
     sim.step_many(1, timed=False)
@@ -313,8 +311,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")
-    ap.add_argument("--density-variant", type=int, default=None)
-    ap.add_argument("--forces-variant", type=int, default=None)
+    ap.add_argument("--neighbour-variant", type=int, default=None)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -35,6 +35,7 @@ struct sph_context {
     float4 *dp = nullptr, *acc = nullptr;
     int *nb_count = nullptr;
     GridBuffers g{};
+    NbBuffers nb{};
     size_t cells_padded = 0;
     bool s_valid = false;     // S holds the pre-integration snapshot the aux arrays are aligned with
     bool grid_valid = false;  // S is in canonical order, key_s / cell_start valid
@@ -48,7 +49,7 @@ struct sph_context {
     cudaGraphExec_t graph_exec = nullptr;
     uint32_t graph_n = 0;
     uint32_t last_step_n = 0xffffffffu;
-    int opt_density_variant = 0, opt_forces_variant = 0, opt_use_graph = 1, opt_count_neighbours = 1;
+    int opt_neighbour_variant = 1, opt_use_graph = 1, opt_count_neighbours = 1;
     uint64_t kernel_launches = 0, graph_launches = 0, steps = 0;
     std::string err;
     void *pinned_ptr = nullptr;
@@ -99,6 +100,11 @@ Params make_params(const sph_config &c) {
     P.h_d = (double)c.h;
     P.h = c.h;
     P.h2 = c.h * c.h;  // fp32 product, as CParticle::h * CParticle::h
+    P.hbx_f = (float)P.hbx;
+    P.hby_f = (float)P.hby;
+    P.hbz_f = (float)P.hbz;
+    P.neg_zero = -0.0f;
+    P.prune_margin = 1e-3f * c.h + 8.0f * 1.2e-7f * std::max(c.box[0], std::max(c.box[1], c.box[2]));
     P.dt = c.dt;
     P.mass = c.mass;
     P.viscosity = c.viscosity;
@@ -152,17 +158,24 @@ void enqueue_grid(sph_context *c) {
     launch_cell_key_hist(c->pos_a, n, c->g, c->P, c->stream);
     launch_scan(c->g, c->stream);
     launch_bucket(c->pos_a, n, c->g, c->stream);
-    launch_rank_scatter(c->pos_a, c->vel_a, c->pos_s, c->vel_s, n, c->g, c->stream);
+    launch_rank_scatter(c->pos_a, c->vel_a, c->pos_s, c->vel_s, n, c->g, c->nb, c->stream);
     c->kernel_launches += 4;
 }
+// variant 1 (default): bitmask passes of sph_neighbours_v2.cu; variant 0: the plain float4 walk of
+// sph_neighbours.cu, also used for grids narrower than 4 cells in x (row over-scan could wrap around)
+bool use_mask_passes(const sph_context *c) { return c->opt_neighbour_variant == 1 && c->P.rx >= 4; }
 void enqueue_density(sph_context *c) {
-    launch_density(c->pos_s, c->g.key_s, c->g.cell_start, c->dp, c->opt_count_neighbours ? c->nb_count : nullptr,
-                   (int)c->n, c->P, c->opt_density_variant, c->stream);
+    if (use_mask_passes(c))
+        launch_density_mask(c->nb, c->vel_s, c->g.key_s, c->g.cell_start, c->dp, c->nb_count, (int)c->n, c->P, c->stream);
+    else
+        launch_density(c->pos_s, c->g.key_s, c->g.cell_start, c->dp, c->nb_count, (int)c->n, c->P, 0, c->stream);
     c->kernel_launches += 1;
 }
 void enqueue_forces(sph_context *c) {
-    launch_forces(c->pos_s, c->vel_s, c->dp, c->g.key_s, c->g.cell_start, c->acc, (int)c->n, c->P,
-                  c->opt_forces_variant, c->stream);
+    if (use_mask_passes(c))
+        launch_forces_mask(c->nb, c->dp, c->nb_count, c->g.key_s, c->g.cell_start, c->acc, (int)c->n, c->P, c->stream);
+    else
+        launch_forces(c->pos_s, c->vel_s, c->dp, c->g.key_s, c->g.cell_start, c->acc, (int)c->n, c->P, 0, c->stream);
     c->kernel_launches += 1;
 }
 void enqueue_integrate(sph_context *c) {
@@ -251,7 +264,7 @@ int sph_destroy(sph_context *c) {
     drop_graph(c);
     void *ptrs[] = {c->pos_a, c->vel_a, c->pos_s, c->vel_s, c->dp, c->acc, c->nb_count, c->g.key_a, c->g.off_a,
                     c->g.bucket_src, c->g.bucket_id, c->g.key_s, c->g.count, c->g.cell_start, c->g.scan_status,
-                    c->d_stage, c->d_tmp_i32, c->d_tmp_f32, c->d_stats};
+                    c->d_stage, c->d_tmp_i32, c->d_tmp_f32, c->d_stats, c->nb.xs, c->nb.ys, c->nb.zs, c->nb.fdat, c->nb.mask};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->d_flush) cudaFree(c->d_flush);
@@ -319,6 +332,11 @@ int sph_create(const sph_config *cfg, sph_context **out) {
     CTX_TRY(dalloc(&c->g.count, c->cells_padded));
     CTX_TRY(dalloc(&c->g.cell_start, c->cells_padded));
     CTX_TRY(dalloc(&c->g.scan_status, (size_t)c->g.n_tiles + 1));
+    CTX_TRY(dalloc(&c->nb.xs, cap + kSoaPad));
+    CTX_TRY(dalloc(&c->nb.ys, cap + kSoaPad));
+    CTX_TRY(dalloc(&c->nb.zs, cap + kSoaPad));
+    CTX_TRY(dalloc(&c->nb.fdat, 2 * cap));
+    CTX_TRY(dalloc(&c->nb.mask, ((cap + 31) / 32) * (size_t)kMaskWords * 32));
     CTX_TRY(dalloc(&c->d_tmp_i32, cap));
     CTX_TRY(dalloc(&c->d_tmp_f32, cap * 5));
     CTX_TRY(dalloc(&c->d_stats, (size_t)8));
@@ -609,7 +627,6 @@ int sph_download_density_pressure_accel(sph_context *c, float *density, float *p
 int sph_download_neighbours(sph_context *c, int32_t *counts, int32_t *lists, uint64_t lists_capacity, uint64_t *total) {
     REQUIRE(c, c && counts, SPH_ERR_ARGUMENT, "sph_download_neighbours: NULL argument");
     REQUIRE(c, c->grid_valid && c->density_valid, SPH_ERR_STATE, "sph_download_neighbours: run sph_density_pressure first");
-    REQUIRE(c, c->opt_count_neighbours, SPH_ERR_STATE, "sph_download_neighbours: option count_neighbours is off");
     CUDA_TRY(c, cudaSetDevice(c->device));
     const size_t n = c->n;
     launch_scatter_by_id_i32(c->pos_s, c->nb_count, c->d_tmp_i32, (int)n, c->stream);
@@ -719,8 +736,7 @@ int sph_stats(sph_context *c, double *out6) {
 int sph_set_option(sph_context *c, const char *name, int value) {
     REQUIRE(c, c && name, SPH_ERR_ARGUMENT, "sph_set_option: NULL argument");
     const std::string k(name);
-    if (k == "density_variant") c->opt_density_variant = value;
-    else if (k == "forces_variant") c->opt_forces_variant = value;
+    if (k == "neighbour_variant") c->opt_neighbour_variant = value;
     else if (k == "use_graph") c->opt_use_graph = value;
     else if (k == "count_neighbours") c->opt_count_neighbours = value;
     else if (k == "flush_l2") { c->opt_flush_l2 = value; return SPH_OK; }

@@ -24,6 +24,9 @@ struct Params {
     double hbx, hby, hbz; // double(box)/2.0           (src/CCPUParticleSimulator.cpp:46-48)
     double h_d;           // double(h)
     float h, h2;          // h2 = fl32(h*h) == 0x3b08df0c
+    float hbx_f, hby_f, hbz_f;  // float(half box): cell-face positions for the conservative row pruning
+    float prune_margin;         // slack (1e-3 h) that makes the pruning bounds safe under fp32 rounding
+    float neg_zero;             // -0.0f as a RUNTIME value: fma(d, d, -0) == fl(d*d), and ptxas cannot re-fuse it (see v2)
     float dt;
     float mass, viscosity, gas_stiffness, rest_density;
     float poly6_f, spiky_f, visc_f;  // fp64 coefficients rounded once to fp32

@@ -148,9 +148,14 @@ __global__ void __launch_bounds__(256) k_rank_scatter(const float4 *__restrict__
                                                       int *__restrict__ key_s, int n, const int *__restrict__ key_a,
                                                       const int *__restrict__ cell_start,
                                                       const int *__restrict__ bucket_src,
-                                                      const int *__restrict__ bucket_id) {
+                                                      const int *__restrict__ bucket_id, float *__restrict__ xs,
+                                                      float *__restrict__ ys, float *__restrict__ zs) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
+    if (s >= n) {
+        // sentinel tail: the 4-wide candidate loads may run up to 3 entries past the last particle
+        if (xs && s < n + kSoaPad) xs[s] = ys[s] = zs[s] = 1.0e18f;
+        return;
+    }
     const int src = bucket_src[s];
     const int my_id = bucket_id[s];
     const int k = __ldg(key_a + src);
@@ -158,16 +163,22 @@ __global__ void __launch_bounds__(256) k_rank_scatter(const float4 *__restrict__
     int rank = 0;
     for (int t = a; t < b; ++t) rank += (__ldg(bucket_id + t) < my_id);
     const int dst = a + rank;
-    pos_s[dst] = __ldg(pos_a + src);
+    const float4 p = __ldg(pos_a + src);
+    pos_s[dst] = p;
     vel_s[dst] = __ldg(vel_a + src);
     key_s[dst] = k;
+    if (xs) {
+        xs[dst] = p.x;
+        ys[dst] = p.y;
+        zs[dst] = p.z;
+    }
 }
 
 void launch_rank_scatter(const float4 *pos_a, const float4 *vel_a, float4 *pos_s, float4 *vel_s, int n,
-                         const GridBuffers &g, cudaStream_t st) {
+                         const GridBuffers &g, const NbBuffers &nb, cudaStream_t st) {
     if (n <= 0) return;
-    k_rank_scatter<<<(n + 255) / 256, 256, 0, st>>>(pos_a, vel_a, pos_s, vel_s, g.key_s, n, g.key_a, g.cell_start,
-                                                    g.bucket_src, g.bucket_id);
+    k_rank_scatter<<<(n + kSoaPad + 255) / 256, 256, 0, st>>>(pos_a, vel_a, pos_s, vel_s, g.key_s, n, g.key_a,
+                                                              g.cell_start, g.bucket_src, g.bucket_id, nb.xs, nb.ys, nb.zs);
 }
 
 }  // namespace sph

@@ -6,6 +6,15 @@
 namespace sph {
 
 constexpr int kScanTile = 2048;  // cells per scan tile (512 threads x int4)
+constexpr int kMaskWords = 32;   // hit-bitmask words per particle (1024 candidate slots); more -> overflow path
+constexpr int kSoaPad = 64;      // far-away sentinel entries after the last particle of xs/ys/zs
+
+// Extra arrays of the production neighbour passes (sph_neighbours_v2.cu)
+struct NbBuffers {
+    float *xs, *ys, *zs;  // [cap + kSoaPad] canonical-order positions, split SoA (16-byte loads = 4 candidates)
+    float4 *fdat;         // [2*cap] {x,y,z,p/rho^2 | vx,vy,vz,1/rho}: one 256-bit gather per neighbour
+    unsigned *mask;       // [ceil(cap/32)*kMaskWords*32] hit bitmask, warp-transposed: word w of lane l at (w*32 + l)
+};
 
 struct GridBuffers {
     int *key_a;                       // [cap]   cell id in input order
@@ -25,13 +34,17 @@ void launch_cell_key_hist(const float4 *pos_a, int n, const GridBuffers &g, cons
 void launch_scan(const GridBuffers &g, cudaStream_t st);
 void launch_bucket(const float4 *pos_a, int n, const GridBuffers &g, cudaStream_t st);
 void launch_rank_scatter(const float4 *pos_a, const float4 *vel_a, float4 *pos_s, float4 *vel_s, int n,
-                         const GridBuffers &g, cudaStream_t st);
+                         const GridBuffers &g, const NbBuffers &nb, cudaStream_t st);
 
 // neighbour passes on the canonical order
 void launch_density(const float4 *pos_s, const int *key_s, const int *cell_start, float4 *dp, int *nb_count, int n,
                     const Params &P, int variant, cudaStream_t st);
 void launch_forces(const float4 *pos_s, const float4 *vel_s, const float4 *dp, const int *key_s, const int *cell_start,
                    float4 *acc, int n, const Params &P, int variant, cudaStream_t st);
+void launch_density_mask(const NbBuffers &nb, const float4 *vel_s, const int *key_s, const int *cell_start, float4 *dp,
+                         int *nb_count, int n, const Params &P, cudaStream_t st);
+void launch_forces_mask(const NbBuffers &nb, const float4 *dp, const int *nb_count, const int *key_s, const int *cell_start,
+                        float4 *acc, int n, const Params &P, cudaStream_t st);
 void launch_integrate_collide(const float4 *pos_s, const float4 *vel_s, float4 *acc, float4 *pos_out, float4 *vel_out,
                               int n, const Params &P, cudaStream_t st);
 

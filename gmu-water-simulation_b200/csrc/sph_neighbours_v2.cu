@@ -1,0 +1,279 @@
+// sph_neighbours_v2.cu — the production neighbour passes (sm_100a):
+//
+//   k_density_mask : one scan of the candidate cells per particle.  Positions come from split SoA
+//                    arrays (xs/ys/zs) with 16-byte loads = 4 candidates per load; the exact,
+//                    un-contracted fp32 predicate r2 <= h2 is evaluated for two candidates per
+//                    instruction with Blackwell's packed fp32x2 ops (FADD2/FMUL2/FFMA2, each element
+//                    rounded to nearest, so the result is bit-identical to the scalar sequence).
+//                    Hits are recorded as a per-particle BITMASK over the candidate enumeration
+//                    (1 predicated bit-insert per candidate instead of a list append) and the
+//                    poly6 density is accumulated branch-free.  Also writes the packed record
+//                    fdat[i] = {x,y,z,p/rho^2 | vx,vy,vz,1/rho} the force pass gathers.
+//   k_forces_mask  : re-derives the same candidate enumeration, walks the set bits and evaluates the
+//                    pressure + viscosity pair term only for true neighbours; each neighbour is ONE
+//                    256-bit gather (LDG.E.ENL2.256, sm_100+).
+//
+// Candidate cells are pruned conservatively per (dy,dz) row: a row is skipped when the particle's
+// distance to the row already exceeds h, and the x-extent is clipped to the cells the h-sphere can
+// reach (keeps ~20.6 of 27 cells on average).  The bounds carry a safety margin, so the neighbour
+// SET is still decided only by the exact predicate.  Rows start at an index aligned down to 4; the
+// up-to-3 extra candidates on either side belong to cells the sphere cannot reach and are masked out
+// of the bitmask word, so counts and sets stay exact.
+#include "sph_kernels.h"
+
+namespace sph {
+
+typedef unsigned long long u64;
+
+// ---- packed fp32x2 helpers (PTX ISA 8.6+, sm_100+) --------------------------------------------
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// h2 - ((dx*dx + dy*dy) + dz*dz) for two candidates, every operation rounded separately.
+// ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even though both carry an explicit .rn
+// (and regardless of -fmad=false), which would change the predicate.  The squares are therefore formed
+// as fma(d, d, -0.0) with the -0.0 coming from a kernel parameter: one rounding of the exact product,
+// i.e. fl(d*d) bit for bit, and an FFMA2 result cannot be contracted into the following FADD2.
+__device__ __forceinline__ u64 t_exact2(u64 px, u64 py, u64 pz, u64 x, u64 y, u64 z, u64 h2, u64 nz) {
+    const u64 dx = sub2(px, x), dy = sub2(py, y), dz = sub2(pz, z);
+    return sub2(h2, add2(add2(fma2(dx, dx, nz), fma2(dy, dy, nz)), fma2(dz, dz, nz)));
+}
+
+__device__ __forceinline__ void ld256(const float4 *p, float4 &a, float4 &b) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+}
+
+// ---- pruned row enumeration, shared by both kernels -------------------------------------------
+// Every floating-point step uses explicit round-to-nearest intrinsics: both kernels must derive
+// exactly the same ranges, so nothing here may be contracted differently by the compiler.
+template <typename F>
+__device__ __forceinline__ void for_each_pruned_row(const float px, const float py, const float pz, const int key,
+                                                    const int *__restrict__ cell_start, const Params &P, F &&f) {
+    const int rxy = P.rx * P.ry;
+    const int cz = key / rxy;
+    const int rem = key - cz * rxy;
+    const int cy = rem / P.rx;
+    const int cx = rem - cy * P.rx;
+    const float m = P.prune_margin, h = P.h;
+    // distances from the particle to the faces of its own cell (negative / large if it was clamped)
+    const float x_lo = __fmaf_rn((float)cx, h, -P.hbx_f), y_lo = __fmaf_rn((float)cy, h, -P.hby_f),
+                z_lo = __fmaf_rn((float)cz, h, -P.hbz_f);
+    const float fx_lo = __fsub_rn(px, x_lo), fx_hi = __fsub_rn(__fadd_rn(x_lo, h), px);
+    const float ey_lo = fmaxf(__fsub_rn(__fsub_rn(py, y_lo), m), 0.0f);
+    const float ey_hi = fmaxf(__fsub_rn(__fsub_rn(__fadd_rn(y_lo, h), py), m), 0.0f);
+    const float ez_lo = fmaxf(__fsub_rn(__fsub_rn(pz, z_lo), m), 0.0f);
+    const float ez_hi = fmaxf(__fsub_rn(__fsub_rn(__fadd_rn(z_lo, h), pz), m), 0.0f);
+    const float dy2_lo = __fmul_rn(ey_lo, ey_lo), dy2_hi = __fmul_rn(ey_hi, ey_hi);
+    const float dz2_lo = __fmul_rn(ez_lo, ez_lo), dz2_hi = __fmul_rn(ez_hi, ez_hi);
+#pragma unroll 1
+    for (int dz = -1; dz <= 1; ++dz) {
+        const int z = cz + dz;
+        if (z < 0 || z >= P.rz) continue;
+        const float dz2 = dz < 0 ? dz2_lo : (dz > 0 ? dz2_hi : 0.0f);
+#pragma unroll 1
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int y = cy + dy;
+            if (y < 0 || y >= P.ry) continue;
+            const float dy2 = dy < 0 ? dy2_lo : (dy > 0 ? dy2_hi : 0.0f);
+            const float rem2 = __fsub_rn(__fsub_rn(P.h2, dy2), dz2);
+            if (rem2 < 0.0f) continue;  // the h-sphere does not reach this row
+            const float wx = __fadd_rn(__fsqrt_rn(rem2), m);
+            const int xl = max(fx_lo < wx ? cx - 1 : cx, 0);
+            const int xr = min(fx_hi < wx ? cx + 1 : cx, P.rx - 1);
+            const int c0 = xl + y * P.rx + z * rxy;
+            const int a = __ldg(cell_start + c0);
+            const int b = __ldg(cell_start + c0 + (xr - xl) + 1);
+            f(a, b);
+        }
+    }
+}
+
+// ================================================================= density + pressure + hit bitmask
+__global__ void __launch_bounds__(128) k_density_mask(const float *__restrict__ xs, const float *__restrict__ ys,
+                                                      const float *__restrict__ zs, const float4 *__restrict__ vel,
+                                                      const int *__restrict__ key, const int *__restrict__ cell_start,
+                                                      float4 *__restrict__ dp, float4 *__restrict__ fdat,
+                                                      unsigned *__restrict__ mask, int *__restrict__ nb_count, int n,
+                                                      const __grid_constant__ Params P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float px = __ldg(xs + i), py = __ldg(ys + i), pz = __ldg(zs + i);
+    const u64 px2 = pk(px, px), py2 = pk(py, py), pz2 = pk(pz, pz), h22 = pk(P.h2, P.h2);
+    const u64 nz2 = pk(P.neg_zero, P.neg_zero);
+    unsigned *const wbase = mask + ((size_t)(i >> 5) * kMaskWords) * 32 + (i & 31);
+    u64 sum_a = 0ull, sum_b = 0ull;  // two packed accumulators (+0.0f, +0.0f)
+    int cnt = 0, widx = 0;
+    for_each_pruned_row(px, py, pz, __ldg(key + i), cell_start, P, [&](const int a, const int b) {
+        int j = a & ~3;
+        while (j < b) {
+            const int jw = j;
+            const int jend = min(jw + 32, b);
+            unsigned m = 0;
+            int pos = 0;
+#pragma unroll 2
+            for (; j < jend; j += 4, pos += 4) {
+                const ulonglong2 X = __ldg(reinterpret_cast<const ulonglong2 *>(xs + j));
+                const ulonglong2 Y = __ldg(reinterpret_cast<const ulonglong2 *>(ys + j));
+                const ulonglong2 Z = __ldg(reinterpret_cast<const ulonglong2 *>(zs + j));
+                const u64 t01 = t_exact2(px2, py2, pz2, X.x, Y.x, Z.x, h22, nz2);
+                const u64 t23 = t_exact2(px2, py2, pz2, X.y, Y.y, Z.y, h22, nz2);
+                float t0, t1, t2, t3;
+                upk(t01, t0, t1);
+                upk(t23, t2, t3);
+                // sign(t) is exact: t >= 0  <=>  r2 <= h2 (NaN compares false, like the reference)
+                const unsigned nib = (t0 >= 0.0f ? 1u : 0u) | (t1 >= 0.0f ? 2u : 0u) | (t2 >= 0.0f ? 4u : 0u) |
+                                     (t3 >= 0.0f ? 8u : 0u);
+                m |= nib << pos;
+                // poly6: sum += max(t,0)^3, branch-free (out-of-range candidates contribute exactly 0 or, on
+                // the r == h knife edge, less than 2^-60 of the self term)
+                const u64 c01 = pk(fmaxf(t0, 0.0f), fmaxf(t1, 0.0f)), c23 = pk(fmaxf(t2, 0.0f), fmaxf(t3, 0.0f));
+                sum_a = fma2(c01, mul2(c01, c01), sum_a);
+                sum_b = fma2(c23, mul2(c23, c23), sum_b);
+            }
+            // keep only the bits of candidates inside [a, b)
+            const int lo = max(a - jw, 0), hi = b - jw;
+            unsigned vm = 0xffffffffu << lo;
+            if (hi < 32) vm &= (1u << hi) - 1u;
+            m &= vm;
+            cnt += __popc(m);
+            if (widx < kMaskWords) wbase[widx * 32] = m;
+            ++widx;
+        }
+    });
+    float s0, s1, s2, s3;
+    upk(sum_a, s0, s1);
+    upk(sum_b, s2, s3);
+    const float sum = (s0 + s1) + (s2 + s3);
+    // Wpoly6 summed, then rho *= mass; p = k (rho - rho0)   (src/CCPUParticleSimulator.cpp:9-15,133-134)
+    float rho = sum * P.poly6_f;
+    rho *= P.mass;
+    const float prs = P.gas_stiffness * (rho - P.rest_density);
+    const float inv_rho = 1.0f / rho;
+    const float A = prs * inv_rho * inv_rho;
+    dp[i] = make_float4(rho, prs, A, inv_rho);
+    const float4 v = __ldg(vel + i);
+    fdat[2 * (size_t)i] = make_float4(px, py, pz, A);
+    fdat[2 * (size_t)i + 1] = make_float4(v.x, v.y, v.z, inv_rho);
+    nb_count[i] = widx > kMaskWords ? (cnt | (int)0x80000000) : cnt;
+}
+
+void launch_density_mask(const NbBuffers &nb, const float4 *vel_s, const int *key_s, const int *cell_start, float4 *dp,
+                         int *nb_count, int n, const Params &P, cudaStream_t st) {
+    if (n <= 0) return;
+    k_density_mask<<<(n + 127) / 128, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, vel_s, key_s, cell_start, dp, nb.fdat, nb.mask,
+                                                    nb_count, n, P);
+}
+
+// ================================================================= forces from the bitmask
+struct ForceSum {
+    float px, py, pz, vx, vy, vz;
+};
+
+// Pair term (src/CCPUParticleSimulator.cpp:17-30,174-186).  `self` zeroes 1/r so the particle's own
+// bit (r = 0) contributes nothing.
+__device__ __forceinline__ void pair_term(ForceSum &f, const float4 pi, const float4 vi, const float4 pj, const float4 vj,
+                                          const bool self, const Params &P) {
+    const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const float inv_r = self ? 0.0f : rsqrtf(r2);
+    const float r = r2 * inv_r;
+    const float hr = P.h - r;
+    const float g = (P.spiky_f * hr) * (hr * inv_r) * (pi.w + pj.w);
+    f.px = fmaf(g, dx, f.px);
+    f.py = fmaf(g, dy, f.py);
+    f.pz = fmaf(g, dz, f.pz);
+    const float l = (P.visc_f * hr) * vj.w;
+    f.vx = fmaf(l, vj.x - vi.x, f.vx);
+    f.vy = fmaf(l, vj.y - vi.y, f.vy);
+    f.vz = fmaf(l, vj.z - vi.z, f.vz);
+}
+
+// Slow path for a particle whose candidate enumeration did not fit the bitmask (> kMaskWords words):
+// walk all 27 cells with the exact predicate, like the variant-0 kernel.
+__device__ __noinline__ void forces_overflow_path(ForceSum &f, const int i, const float4 pi, const float4 vi, const int key,
+                                                  const float *__restrict__ xs, const float *__restrict__ ys,
+                                                  const float *__restrict__ zs, const float4 *__restrict__ fdat,
+                                                  const int *__restrict__ cell_start, const Params &P) {
+    for_each_row(key, cell_start, P, [&](int a, int b) {
+        for (int j = a; j < b; ++j) {
+            const float r2 = r2_exact(pi.x - __ldg(xs + j), pi.y - __ldg(ys + j), pi.z - __ldg(zs + j));
+            if (P.h2 - r2 >= 0.0f && j != i) {
+                float4 pj, vj;
+                ld256(fdat + 2 * (size_t)j, pj, vj);
+                pair_term(f, pi, vi, pj, vj, false, P);
+            }
+        }
+    });
+}
+
+__global__ void __launch_bounds__(128) k_forces_mask(const float *__restrict__ xs, const float *__restrict__ ys,
+                                                     const float *__restrict__ zs, const float4 *__restrict__ fdat,
+                                                     const float4 *__restrict__ dp, const unsigned *__restrict__ mask,
+                                                     const int *__restrict__ nb_count, const int *__restrict__ key,
+                                                     const int *__restrict__ cell_start, float4 *__restrict__ acc, int n,
+                                                     const __grid_constant__ Params P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 pi, vi;
+    ld256(fdat + 2 * (size_t)i, pi, vi);
+    const int k = __ldg(key + i);
+    ForceSum f = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (__ldg(nb_count + i) < 0) {
+        forces_overflow_path(f, i, pi, vi, k, xs, ys, zs, fdat, cell_start, P);
+    } else {
+        const unsigned *const wbase = mask + ((size_t)(i >> 5) * kMaskWords) * 32 + (i & 31);
+        int widx = 0;
+        for_each_pruned_row(pi.x, pi.y, pi.z, k, cell_start, P, [&](const int a, const int b) {
+            for (int jw = a & ~3; jw < b; jw += 32) {
+                unsigned m = __ldg(wbase + widx * 32);
+                ++widx;
+                while (m) {
+                    const int j = jw + __ffs(m) - 1;
+                    m &= m - 1;
+                    float4 pj, vj;
+                    ld256(fdat + 2 * (size_t)j, pj, vj);
+                    pair_term(f, pi, vi, pj, vj, j == i, P);
+                }
+            }
+        });
+    }
+    // f_p *= -m rho_i ; f_v *= mu m ; a = (f_p + f_v + g rho_i) / rho_i   (src/CCPUParticleSimulator.cpp:191-195)
+    const float rho = __ldg(&dp[i].x);
+    const float sp = -P.mass * rho, sv = P.viscosity * P.mass;
+    acc[i] = make_float4((f.px * sp + f.vx * sv + P.gx * rho) / rho, (f.py * sp + f.vy * sv + P.gy * rho) / rho,
+                         (f.pz * sp + f.vz * sv + P.gz * rho) / rho, 0.0f);
+}
+
+void launch_forces_mask(const NbBuffers &nb, const float4 *dp, const int *nb_count, const int *key_s, const int *cell_start,
+                        float4 *acc, int n, const Params &P, cudaStream_t st) {
+    if (n <= 0) return;
+    k_forces_mask<<<(n + 127) / 128, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, nb.fdat, dp, nb.mask, nb_count, key_s, cell_start,
+                                                   acc, n, P);
+}
+
+}  // namespace sph

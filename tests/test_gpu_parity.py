@@ -24,10 +24,18 @@ def state_after(box, steps, scenario=DAM_BREAK):
     return o
 
 
-def make_ctx(gws, box, pos, vel, cap=None):
+def make_ctx(gws, box, pos, vel, cap=None, variant=1):
     ctx = gws.SphContext(box, cap or max(len(pos), 1))
+    ctx.set_option("neighbour_variant", variant)  # 1 = bitmask passes (production), 0 = plain float4 walk
     ctx.upload(gws.particles_from_arrays(pos, vel))
     return ctx
+
+
+def pos_tolerance(o):
+    """One step from identical inputs: dx = a dt^2 carries the acceleration tolerance, plus a few ulps."""
+    dt2 = 1e-4
+    a_tol = RTOL * np.maximum(np.linalg.norm(o.acc, axis=1), o.acc_scale)
+    return (a_tol * dt2 + 4 * np.spacing(np.abs(o.pos).max(axis=1).astype(np.float32)))[:, None]
 
 
 def check_density(o, rho, prs):
@@ -42,10 +50,10 @@ def check_acc(ref, scale, got):
     assert np.all(err <= tol), f"worst acc error/tol = {(err / tol).max():.3f}"
 
 
-def phase_parity(gws, o, box):
+def phase_parity(gws, o, box, variant=1):
     """One step of both implementations from the oracle's current state, checked phase by phase."""
     pos, vel = o.pos, o.vel
-    ctx = make_ctx(gws, box, pos, vel)
+    ctx = make_ctx(gws, box, pos, vel, variant=variant)
     # ---- grid
     o.update_grid()
     ctx.update_grid()
@@ -82,22 +90,33 @@ def phase_parity(gws, o, box):
     assert np.array_equal(rec["position"][:, :3].view(np.uint32), new_pos.view(np.uint32))
     assert np.array_equal(rec["velocity"][:, :3].view(np.uint32), new_vel.view(np.uint32))
     # and against the oracle's own integration within the acceleration tolerance
+    tol = pos_tolerance(o)
     o.integrate()
-    assert np.abs(rec["position"][:, :3] - o.pos).max() <= 1e-4 * 0.0457
+    assert np.all(np.abs(rec["position"][:, :3] - o.pos) <= tol)
     # the record also carries this step's density/pressure/cell id, like the reference's read-back
     assert np.array_equal(rec["cell_id"].astype(np.int32), ctx.keys())
     assert np.array_equal(rec["density"], rho)
     ctx.close()
 
 
-@pytest.mark.parametrize("box,steps", [(0.4, 0), (0.4, 1), (0.4, 10), (0.4, 100), (0.9, 0), (0.9, 25)])
-def test_phase_parity_dam_break(gws, box, steps):
-    phase_parity(gws, state_after(box, steps), box)
+@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("box,steps", [(0.4, 0), (0.4, 1), (0.4, 10), (0.4, 100), (0.9, 0), (0.9, 25), (0.2, 30), (0.1, 5)])
+def test_phase_parity_dam_break(gws, box, steps, variant):
+    # step 0 is the knife-edge case: thousands of lattice pairs sit at r == h exactly;
+    # boxes 0.1/0.2 have grids narrower than 4 cells (the library falls back to the plain walk there)
+    phase_parity(gws, state_after(box, steps), box, variant)
 
 
-def test_phase_parity_non_cubic_box(gws):
+@pytest.mark.parametrize("variant", [1, 0])
+def test_phase_parity_non_cubic_box(gws, variant):
     box = (0.5, 0.3, 0.7)
-    phase_parity(gws, state_after(box, 12), box)
+    phase_parity(gws, state_after(box, 12), box, variant)
+
+
+@pytest.mark.parametrize("steps", [1, 40, 150])
+def test_phase_parity_fountain_state(gws, steps):
+    """Per-phase parity on fountain states (particles emitted on the floor plane, strong wall forces)."""
+    phase_parity(gws, state_after(0.4, steps, FOUNTAIN), 0.4)
 
 
 def test_phase_parity_golden_fixture(gws):
@@ -200,8 +219,15 @@ def test_fountain_through_simulator(gws):
     sim.sync_host()
     hp = sim.host_particles()
     assert sim.n == o.n == 7 * steps
-    assert np.abs(hp["position"][:, :3] - o.pos).max() <= 2e-4 * 0.0457
-    assert np.abs(hp["velocity"][:, :3] - o.vel).max() <= 1e-3
+    assert np.array_equal(hp["id"], np.arange(sim.n, dtype=np.uint32))
+    # the newest batch has only been integrated once: tight; older particles have been through up to 40
+    # steps of a chaotic system (accelerations of 1e3..1e4 m/s^2 at the nozzle), so compare statistically
+    err = np.abs(hp["position"][:, :3] - o.pos).max(axis=1)
+    assert err[-7:].max() <= 1e-5
+    assert np.percentile(err, 95) <= 0.0457 and np.isfinite(hp["position"]).all()
+    assert np.abs(hp["position"][:, :3].mean(axis=0) - o.pos.mean(axis=0)).max() <= 0.1 * 0.0457
+    ke_g = 0.5 * 0.02 * (hp["velocity"][:, :3].astype(np.float64) ** 2).sum()
+    assert abs(ke_g / o.stats()["ke"] - 1) <= 0.05
 
 
 def test_simulator_phase_path_and_mirror_modes(gws):
@@ -260,12 +286,14 @@ def test_edge_cases(gws):
     assert np.array_equal(np.sort(ctx.permutation()), np.arange(5))
 
 
-def test_dense_cell_overflow_path(gws):
-    """More neighbours than the force kernel's hit queue holds (very dense clump): overflow path."""
+@pytest.mark.parametrize("variant,n_clump", [(0, 400), (1, 400), (1, 1500)])
+def test_dense_cell_overflow_path(gws, variant, n_clump):
+    """Very dense clump: more hits than the variant-0 queue holds (400) and more candidates than the
+    1024-slot hit bitmask of the production kernels holds (1500) -> their overflow paths."""
     rng = np.random.default_rng(1234)
-    pos = (rng.random((400, 3), dtype=np.float32) - 0.5) * np.float32(0.03)
+    pos = (rng.random((n_clump, 3), dtype=np.float32) - 0.5) * np.float32(0.03)
     o = Oracle(0.4).set_state(pos)
-    ctx = make_ctx(gws, 0.4, pos, np.zeros_like(pos))
+    ctx = make_ctx(gws, 0.4, pos, np.zeros_like(pos), variant=variant)
     o.update_grid(); o.update_density_pressure(); o.update_forces()
     ctx.update_grid(); ctx.density_pressure(); ctx.forces()
     oc, ol = o.neighbours(); gc, gl = ctx.neighbours()

@@ -11,14 +11,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--box", type=float, default=3.62)
 ap.add_argument("--preroll", type=int, default=200)
 ap.add_argument("--steps", type=int, default=3)
-ap.add_argument("--density-variant", type=int, default=0)
-ap.add_argument("--forces-variant", type=int, default=0)
+ap.add_argument("--neighbour-variant", type=int, default=1)
 a = ap.parse_args()
 sim = gws.Simulator("cuda", a.box).setup_scene()
 ctx = sim.context()
 ctx.set_option("use_graph", 0)
-ctx.set_option("density_variant", a.density_variant)
-ctx.set_option("forces_variant", a.forces_variant)
+ctx.set_option("neighbour_variant", a.neighbour_variant)
 for _ in range(a.preroll):
     ctx.step(1, timed=False)
 ctx.synchronize()
