@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(128) k_density_mask(const float *__restrict__ 
     const u64 nz2 = pk(P.neg_zero, P.neg_zero);
     unsigned *const wbase = mask + ((size_t)(i >> 5) * kMaskWords) * 32 + (i & 31);
     u64 sum_a = 0ull, sum_b = 0ull;  // two packed accumulators (+0.0f, +0.0f)
+    float stray_sum = 0.0f;
     int cnt = 0, widx = 0;
     for_each_pruned_row(px, py, pz, __ldg(key + i), cell_start, P, [&](const int a, const int b) {
         int j = a & ~3;
@@ -149,8 +150,7 @@ __global__ void __launch_bounds__(128) k_density_mask(const float *__restrict__ 
                 const unsigned nib = (t0 >= 0.0f ? 1u : 0u) | (t1 >= 0.0f ? 2u : 0u) | (t2 >= 0.0f ? 4u : 0u) |
                                      (t3 >= 0.0f ? 8u : 0u);
                 m |= nib << pos;
-                // poly6: sum += max(t,0)^3, branch-free (out-of-range candidates contribute exactly 0 or, on
-                // the r == h knife edge, less than 2^-60 of the self term)
+                // poly6: sum += max(t,0)^3, branch-free
                 const u64 c01 = pk(fmaxf(t0, 0.0f), fmaxf(t1, 0.0f)), c23 = pk(fmaxf(t2, 0.0f), fmaxf(t3, 0.0f));
                 sum_a = fma2(c01, mul2(c01, c01), sum_a);
                 sum_b = fma2(c23, mul2(c23, c23), sum_b);
@@ -159,7 +159,19 @@ __global__ void __launch_bounds__(128) k_density_mask(const float *__restrict__ 
             const int lo = max(a - jw, 0), hi = b - jw;
             unsigned vm = 0xffffffffu << lo;
             if (hi < 32) vm &= (1u << hi) - 1u;
+            // The <= 3 slots scanned before a / after b hold whatever particles are adjacent in the sorted
+            // array — usually cells the sphere cannot reach, but next to empty cells they can be true
+            // neighbours that another row already counts.  Their bits are dropped here; their (rare) density
+            // contribution is recomputed exactly and taken out again at the end.
+            unsigned stray = m & ~vm;
             m &= vm;
+            while (stray) {
+                const int js = jw + __ffs(stray) - 1;
+                stray &= stray - 1;
+                const float ts = P.h2 - r2_exact(px - __ldg(xs + js), py - __ldg(ys + js), pz - __ldg(zs + js));
+                const float cs = fmaxf(ts, 0.0f);
+                stray_sum = fmaf(cs * cs, cs, stray_sum);
+            }
             cnt += __popc(m);
             if (widx < kMaskWords) wbase[widx * 32] = m;
             ++widx;
@@ -168,7 +180,7 @@ __global__ void __launch_bounds__(128) k_density_mask(const float *__restrict__ 
     float s0, s1, s2, s3;
     upk(sum_a, s0, s1);
     upk(sum_b, s2, s3);
-    const float sum = (s0 + s1) + (s2 + s3);
+    const float sum = ((s0 + s1) + (s2 + s3)) - stray_sum;
     // Wpoly6 summed, then rho *= mass; p = k (rho - rho0)   (src/CCPUParticleSimulator.cpp:9-15,133-134)
     float rho = sum * P.poly6_f;
     rho *= P.mass;
