@@ -264,7 +264,7 @@ int sph_destroy(sph_context *c) {
     drop_graph(c);
     void *ptrs[] = {c->pos_a, c->vel_a, c->pos_s, c->vel_s, c->dp, c->acc, c->nb_count, c->g.key_a, c->g.off_a,
                     c->g.bucket_src, c->g.bucket_id, c->g.key_s, c->g.count, c->g.cell_start, c->g.scan_status,
-                    c->d_stage, c->d_tmp_i32, c->d_tmp_f32, c->d_stats, c->nb.xs, c->nb.ys, c->nb.zs, c->nb.fdat, c->nb.mask};
+                    c->d_stage, c->d_tmp_i32, c->d_tmp_f32, c->d_stats, c->nb.xs, c->nb.ys, c->nb.zs, c->nb.fdat, c->nb.mask, c->nb.words};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->d_flush) cudaFree(c->d_flush);
@@ -337,6 +337,7 @@ int sph_create(const sph_config *cfg, sph_context **out) {
     CTX_TRY(dalloc(&c->nb.zs, cap + kSoaPad));
     CTX_TRY(dalloc(&c->nb.fdat, 2 * cap));
     CTX_TRY(dalloc(&c->nb.mask, ((cap + 31) / 32) * (size_t)kMaskWords * 32));
+    CTX_TRY(dalloc(&c->nb.words, cap));
     CTX_TRY(dalloc(&c->d_tmp_i32, cap));
     CTX_TRY(dalloc(&c->d_tmp_f32, cap * 5));
     CTX_TRY(dalloc(&c->d_stats, (size_t)8));

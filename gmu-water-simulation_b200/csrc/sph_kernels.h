@@ -6,14 +6,16 @@
 namespace sph {
 
 constexpr int kScanTile = 2048;  // cells per scan tile (512 threads x int4)
-constexpr int kMaskWords = 32;   // hit-bitmask words per particle (1024 candidate slots); more -> overflow path
+constexpr int kMaskWords = 32;   // stored (non-empty) hit words per particle; more -> overflow path
 constexpr int kSoaPad = 64;      // far-away sentinel entries after the last particle of xs/ys/zs
 
 // Extra arrays of the production neighbour passes (sph_neighbours_v2.cu)
 struct NbBuffers {
     float *xs, *ys, *zs;  // [cap + kSoaPad] canonical-order positions, split SoA (16-byte loads = 4 candidates)
     float4 *fdat;         // [2*cap] {x,y,z,p/rho^2 | vx,vy,vz,1/rho}: one 256-bit gather per neighbour
-    unsigned *mask;       // [ceil(cap/32)*kMaskWords*32] hit bitmask, warp-transposed: word w of lane l at (w*32 + l)
+    uint2 *mask;          // [ceil(cap/32)*kMaskWords*32] hit words {bits, first candidate + 31}, warp-transposed:
+                          // word w of lane l of warp q at (q*kMaskWords + w)*32 + l
+    int *words;           // [cap] number of non-empty hit words of each particle (> kMaskWords = overflow)
 };
 
 struct GridBuffers {

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) k_scatter_by_id_i32(const float4 *__restr
                                                            int *__restrict__ dst, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    dst[__float_as_int(__ldg(&pos[i].w))] = src[i] & 0x7fffffff;  // (neighbour counts carry an overflow flag in bit 31)
+    dst[__float_as_int(__ldg(&pos[i].w))] = src[i];
 }
 void launch_scatter_by_id_i32(const float4 *pos, const int *src, int *dst_by_id, int n, cudaStream_t st) {
     if (n <= 0) return;

@@ -1,24 +1,24 @@
 // sph_neighbours_v2.cu — the production neighbour passes (sm_100a):
 //
-//   k_density_mask : one scan of the candidate cells per particle.  Positions come from split SoA
-//                    arrays (xs/ys/zs) with 16-byte loads = 4 candidates per load; the exact,
-//                    un-contracted fp32 predicate r2 <= h2 is evaluated for two candidates per
-//                    instruction with Blackwell's packed fp32x2 ops (FADD2/FMUL2/FFMA2, each element
-//                    rounded to nearest, so the result is bit-identical to the scalar sequence).
-//                    Hits are recorded as a per-particle BITMASK over the candidate enumeration
-//                    (1 predicated bit-insert per candidate instead of a list append) and the
-//                    poly6 density is accumulated branch-free.  Also writes the packed record
+//   k_density_mask : one scan of the 27 candidate cells (<= 9 contiguous rows) per particle.  Positions
+//                    come from split SoA arrays (xs/ys/zs) with 16-byte loads = 4 candidates per load;
+//                    the exact, un-contracted fp32 predicate r2 <= h2 is evaluated for two candidates
+//                    per instruction with Blackwell's packed fp32x2 ops (FADD2/FFMA2, each element
+//                    rounded to nearest: bit-identical to the scalar sequence).  Hits are recorded as
+//                    a BITMASK: the sign bit of t = h2 - r2 is funnel-shifted into a 32-candidate word
+//                    (one SHF per candidate, no predicate -> bit conversion, no list append), and the
+//                    poly6 density is accumulated branch-free.  Each finished word is stored with the
+//                    index of its first candidate.  Also writes the packed record
 //                    fdat[i] = {x,y,z,p/rho^2 | vx,vy,vz,1/rho} the force pass gathers.
-//   k_forces_mask  : re-derives the same candidate enumeration, walks the set bits and evaluates the
-//                    pressure + viscosity pair term only for true neighbours; each neighbour is ONE
-//                    256-bit gather (LDG.E.ENL2.256, sm_100+).
+//   k_forces_mask  : walks the set bits of the particle's words as ONE flat loop (no per-row or
+//                    per-word lock-step across the warp) and evaluates the pressure + viscosity pair
+//                    term for true neighbours only; each neighbour is ONE 256-bit gather
+//                    (LDG.E.ENL2.256, sm_100+).
 //
-// Candidate cells are pruned conservatively per (dy,dz) row: a row is skipped when the particle's
-// distance to the row already exceeds h, and the x-extent is clipped to the cells the h-sphere can
-// reach (keeps ~20.6 of 27 cells on average).  The bounds carry a safety margin, so the neighbour
-// SET is still decided only by the exact predicate.  Rows start at an index aligned down to 4; the
-// up-to-3 extra candidates on either side belong to cells the sphere cannot reach and are masked out
-// of the bitmask word, so counts and sets stay exact.
+// Rows start at an index aligned down to 4 and end aligned up; the <= 3 extra slots on either side
+// are masked out of the word (and their rare density contribution is taken out again), so counts and
+// sets stay exact.  (Per-particle geometric pruning of rows/cells was measured and dropped: under
+// SIMT a warp pays for its longest lane, so it only lowered lane utilisation.)
 #include "sph_kernels.h"
 
 namespace sph {
@@ -68,76 +68,33 @@ __device__ __forceinline__ void ld256(const float4 *p, float4 &a, float4 &b) {
         : "l"(p));
 }
 
-// ---- pruned row enumeration, shared by both kernels -------------------------------------------
-// Every floating-point step uses explicit round-to-nearest intrinsics: both kernels must derive
-// exactly the same ranges, so nothing here may be contracted differently by the compiler.
-template <typename F>
-__device__ __forceinline__ void for_each_pruned_row(const float px, const float py, const float pz, const int key,
-                                                    const int *__restrict__ cell_start, const Params &P, F &&f) {
-    const int rxy = P.rx * P.ry;
-    const int cz = key / rxy;
-    const int rem = key - cz * rxy;
-    const int cy = rem / P.rx;
-    const int cx = rem - cy * P.rx;
-    const float m = P.prune_margin, h = P.h;
-    // distances from the particle to the faces of its own cell (negative / large if it was clamped)
-    const float x_lo = __fmaf_rn((float)cx, h, -P.hbx_f), y_lo = __fmaf_rn((float)cy, h, -P.hby_f),
-                z_lo = __fmaf_rn((float)cz, h, -P.hbz_f);
-    const float fx_lo = __fsub_rn(px, x_lo), fx_hi = __fsub_rn(__fadd_rn(x_lo, h), px);
-    const float ey_lo = fmaxf(__fsub_rn(__fsub_rn(py, y_lo), m), 0.0f);
-    const float ey_hi = fmaxf(__fsub_rn(__fsub_rn(__fadd_rn(y_lo, h), py), m), 0.0f);
-    const float ez_lo = fmaxf(__fsub_rn(__fsub_rn(pz, z_lo), m), 0.0f);
-    const float ez_hi = fmaxf(__fsub_rn(__fsub_rn(__fadd_rn(z_lo, h), pz), m), 0.0f);
-    const float dy2_lo = __fmul_rn(ey_lo, ey_lo), dy2_hi = __fmul_rn(ey_hi, ey_hi);
-    const float dz2_lo = __fmul_rn(ez_lo, ez_lo), dz2_hi = __fmul_rn(ez_hi, ez_hi);
-#pragma unroll 1
-    for (int dz = -1; dz <= 1; ++dz) {
-        const int z = cz + dz;
-        if (z < 0 || z >= P.rz) continue;
-        const float dz2 = dz < 0 ? dz2_lo : (dz > 0 ? dz2_hi : 0.0f);
-#pragma unroll 1
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int y = cy + dy;
-            if (y < 0 || y >= P.ry) continue;
-            const float dy2 = dy < 0 ? dy2_lo : (dy > 0 ? dy2_hi : 0.0f);
-            const float rem2 = __fsub_rn(__fsub_rn(P.h2, dy2), dz2);
-            if (rem2 < 0.0f) continue;  // the h-sphere does not reach this row
-            const float wx = __fadd_rn(__fsqrt_rn(rem2), m);
-            const int xl = max(fx_lo < wx ? cx - 1 : cx, 0);
-            const int xr = min(fx_hi < wx ? cx + 1 : cx, P.rx - 1);
-            const int c0 = xl + y * P.rx + z * rxy;
-            const int a = __ldg(cell_start + c0);
-            const int b = __ldg(cell_start + c0 + (xr - xl) + 1);
-            f(a, b);
-        }
-    }
-}
-
 // ================================================================= density + pressure + hit bitmask
+// Word format: bit 31 = first candidate of the word (index j0), bit 31-k = candidate j0+k.
+// Stored as uint2 {bits, j0 + 31} so that the force pass gets j = (j0 + 31) - msb_index(bits).
 __global__ void __launch_bounds__(128) k_density_mask(const float *__restrict__ xs, const float *__restrict__ ys,
                                                       const float *__restrict__ zs, const float4 *__restrict__ vel,
                                                       const int *__restrict__ key, const int *__restrict__ cell_start,
                                                       float4 *__restrict__ dp, float4 *__restrict__ fdat,
-                                                      unsigned *__restrict__ mask, int *__restrict__ nb_count, int n,
+                                                      uint2 *__restrict__ mask, int *__restrict__ nb_count,
+                                                      int *__restrict__ nb_words, int n,
                                                       const __grid_constant__ Params P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float px = __ldg(xs + i), py = __ldg(ys + i), pz = __ldg(zs + i);
     const u64 px2 = pk(px, px), py2 = pk(py, py), pz2 = pk(pz, pz), h22 = pk(P.h2, P.h2);
     const u64 nz2 = pk(P.neg_zero, P.neg_zero);
-    unsigned *const wbase = mask + ((size_t)(i >> 5) * kMaskWords) * 32 + (i & 31);
+    uint2 *const wbase = mask + ((size_t)(i >> 5) * kMaskWords) * 32 + (i & 31);
     u64 sum_a = 0ull, sum_b = 0ull;  // two packed accumulators (+0.0f, +0.0f)
     float stray_sum = 0.0f;
     int cnt = 0, widx = 0;
-    for_each_pruned_row(px, py, pz, __ldg(key + i), cell_start, P, [&](const int a, const int b) {
+    for_each_row(__ldg(key + i), cell_start, P, [&](const int a, const int b) {
         int j = a & ~3;
         while (j < b) {
             const int jw = j;
             const int jend = min(jw + 32, b);
-            unsigned m = 0;
-            int pos = 0;
+            unsigned miss = 0;  // sign bits of t, first candidate ends up in the highest bit shifted in
 #pragma unroll 2
-            for (; j < jend; j += 4, pos += 4) {
+            for (; j < jend; j += 4) {
                 const ulonglong2 X = __ldg(reinterpret_cast<const ulonglong2 *>(xs + j));
                 const ulonglong2 Y = __ldg(reinterpret_cast<const ulonglong2 *>(ys + j));
                 const ulonglong2 Z = __ldg(reinterpret_cast<const ulonglong2 *>(zs + j));
@@ -146,35 +103,40 @@ __global__ void __launch_bounds__(128) k_density_mask(const float *__restrict__ 
                 float t0, t1, t2, t3;
                 upk(t01, t0, t1);
                 upk(t23, t2, t3);
-                // sign(t) is exact: t >= 0  <=>  r2 <= h2 (NaN compares false, like the reference)
-                const unsigned nib = (t0 >= 0.0f ? 1u : 0u) | (t1 >= 0.0f ? 2u : 0u) | (t2 >= 0.0f ? 4u : 0u) |
-                                     (t3 >= 0.0f ? 8u : 0u);
-                m |= nib << pos;
+                // t >= 0  <=>  r2 <= h2, and sign(t) is exact (t is never -0): append the sign bits
+                miss = __funnelshift_l(__float_as_uint(t0), miss, 1);
+                miss = __funnelshift_l(__float_as_uint(t1), miss, 1);
+                miss = __funnelshift_l(__float_as_uint(t2), miss, 1);
+                miss = __funnelshift_l(__float_as_uint(t3), miss, 1);
                 // poly6: sum += max(t,0)^3, branch-free
                 const u64 c01 = pk(fmaxf(t0, 0.0f), fmaxf(t1, 0.0f)), c23 = pk(fmaxf(t2, 0.0f), fmaxf(t3, 0.0f));
                 sum_a = fma2(c01, mul2(c01, c01), sum_a);
                 sum_b = fma2(c23, mul2(c23, c23), sum_b);
             }
-            // keep only the bits of candidates inside [a, b)
-            const int lo = max(a - jw, 0), hi = b - jw;
-            unsigned vm = 0xffffffffu << lo;
-            if (hi < 32) vm &= (1u << hi) - 1u;
+            // left-justify (a short last word shifted in fewer than 32 bits), turn misses into hits and keep
+            // only the candidates inside [a, b)
+            const int scanned = j - jw;                       // multiple of 4, 4..32
+            unsigned m = ~(miss << (32 - scanned));
+            const int lo = max(a - jw, 0), hi = min(b - jw, 32);  // valid candidate offsets [lo, hi)
+            const unsigned vm = (0xffffffffu >> lo) & ~((hi < 32) ? (0xffffffffu >> hi) : 0u);
             // The <= 3 slots scanned before a / after b hold whatever particles are adjacent in the sorted
-            // array — usually cells the sphere cannot reach, but next to empty cells they can be true
+            // array - usually cells the sphere cannot reach, but next to empty cells they can be true
             // neighbours that another row already counts.  Their bits are dropped here; their (rare) density
             // contribution is recomputed exactly and taken out again at the end.
-            unsigned stray = m & ~vm;
+            unsigned stray = m & ~vm & ~((scanned < 32) ? (0xffffffffu >> scanned) : 0u);
             m &= vm;
             while (stray) {
-                const int js = jw + __ffs(stray) - 1;
-                stray &= stray - 1;
+                const int js = jw + __clz(stray);
+                stray &= ~(0x80000000u >> __clz(stray));
                 const float ts = P.h2 - r2_exact(px - __ldg(xs + js), py - __ldg(ys + js), pz - __ldg(zs + js));
                 const float cs = fmaxf(ts, 0.0f);
                 stray_sum = fmaf(cs * cs, cs, stray_sum);
             }
             cnt += __popc(m);
-            if (widx < kMaskWords) wbase[widx * 32] = m;
-            ++widx;
+            if (m) {  // empty words are not stored at all
+                if (widx < kMaskWords) wbase[widx * 32] = make_uint2(m, (unsigned)(jw + 31));
+                ++widx;
+            }
         }
     });
     float s0, s1, s2, s3;
@@ -191,14 +153,15 @@ __global__ void __launch_bounds__(128) k_density_mask(const float *__restrict__ 
     const float4 v = __ldg(vel + i);
     fdat[2 * (size_t)i] = make_float4(px, py, pz, A);
     fdat[2 * (size_t)i + 1] = make_float4(v.x, v.y, v.z, inv_rho);
-    nb_count[i] = widx > kMaskWords ? (cnt | (int)0x80000000) : cnt;
+    nb_count[i] = cnt;
+    nb_words[i] = widx;  // > kMaskWords: the force pass takes the overflow path for this particle
 }
 
 void launch_density_mask(const NbBuffers &nb, const float4 *vel_s, const int *key_s, const int *cell_start, float4 *dp,
                          int *nb_count, int n, const Params &P, cudaStream_t st) {
     if (n <= 0) return;
     k_density_mask<<<(n + 127) / 128, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, vel_s, key_s, cell_start, dp, nb.fdat, nb.mask,
-                                                    nb_count, n, P);
+                                                    nb_count, nb.words, n, P);
 }
 
 // ================================================================= forces from the bitmask
@@ -225,8 +188,8 @@ __device__ __forceinline__ void pair_term(ForceSum &f, const float4 pi, const fl
     f.vz = fmaf(l, vj.z - vi.z, f.vz);
 }
 
-// Slow path for a particle whose candidate enumeration did not fit the bitmask (> kMaskWords words):
-// walk all 27 cells with the exact predicate, like the variant-0 kernel.
+// Slow path for a particle whose hit words did not fit (> kMaskWords non-empty words): walk all 27
+// cells with the exact predicate, like the variant-0 kernel.
 __device__ __noinline__ void forces_overflow_path(ForceSum &f, const int i, const float4 pi, const float4 vi, const int key,
                                                   const float *__restrict__ xs, const float *__restrict__ ys,
                                                   const float *__restrict__ zs, const float4 *__restrict__ fdat,
@@ -245,34 +208,41 @@ __device__ __noinline__ void forces_overflow_path(ForceSum &f, const int i, cons
 
 __global__ void __launch_bounds__(128) k_forces_mask(const float *__restrict__ xs, const float *__restrict__ ys,
                                                      const float *__restrict__ zs, const float4 *__restrict__ fdat,
-                                                     const float4 *__restrict__ dp, const unsigned *__restrict__ mask,
-                                                     const int *__restrict__ nb_count, const int *__restrict__ key,
+                                                     const float4 *__restrict__ dp, const uint2 *__restrict__ mask,
+                                                     const int *__restrict__ nb_words, const int *__restrict__ key,
                                                      const int *__restrict__ cell_start, float4 *__restrict__ acc, int n,
                                                      const __grid_constant__ Params P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 pi, vi;
     ld256(fdat + 2 * (size_t)i, pi, vi);
-    const int k = __ldg(key + i);
     ForceSum f = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (__ldg(nb_count + i) < 0) {
-        forces_overflow_path(f, i, pi, vi, k, xs, ys, zs, fdat, cell_start, P);
+    const int nw = __ldg(nb_words + i);
+    if (nw > kMaskWords) {
+        forces_overflow_path(f, i, pi, vi, __ldg(key + i), xs, ys, zs, fdat, cell_start, P);
     } else {
-        const unsigned *const wbase = mask + ((size_t)(i >> 5) * kMaskWords) * 32 + (i & 31);
-        int widx = 0;
-        for_each_pruned_row(pi.x, pi.y, pi.z, k, cell_start, P, [&](const int a, const int b) {
-            for (int jw = a & ~3; jw < b; jw += 32) {
-                unsigned m = __ldg(wbase + widx * 32);
-                ++widx;
-                while (m) {
-                    const int j = jw + __ffs(m) - 1;
-                    m &= m - 1;
-                    float4 pj, vj;
-                    ld256(fdat + 2 * (size_t)j, pj, vj);
-                    pair_term(f, pi, vi, pj, vj, j == i, P);
-                }
+        // Flat walk: every lane consumes its own stream of set bits; a lane that runs out of bits pulls its
+        // next word (prefetched one ahead), so the warp runs for max(hits) iterations, not sum of per-word maxima.
+        const uint2 *wp = mask + ((size_t)(i >> 5) * kMaskWords) * 32 + (i & 31);
+        const uint2 *const wend = wp + (size_t)nw * 32;
+        uint2 next = nw > 0 ? __ldg(wp) : make_uint2(0u, 0u);
+        unsigned m = 0;
+        int j31 = 0;
+        for (;;) {
+            if (m == 0) {
+                if (wp == wend) break;
+                m = next.x;
+                j31 = (int)next.y;
+                wp += 32;
+                if (wp != wend) next = __ldg(wp);
             }
-        });
+            const int msb = 31 - __clz(m);  // stored words are never empty
+            m &= ~(1u << msb);
+            const int j = j31 - msb;
+            float4 pj, vj;
+            ld256(fdat + 2 * (size_t)j, pj, vj);
+            pair_term(f, pi, vi, pj, vj, j == i, P);
+        }
     }
     // f_p *= -m rho_i ; f_v *= mu m ; a = (f_p + f_v + g rho_i) / rho_i   (src/CCPUParticleSimulator.cpp:191-195)
     const float rho = __ldg(&dp[i].x);
@@ -284,7 +254,8 @@ __global__ void __launch_bounds__(128) k_forces_mask(const float *__restrict__ x
 void launch_forces_mask(const NbBuffers &nb, const float4 *dp, const int *nb_count, const int *key_s, const int *cell_start,
                         float4 *acc, int n, const Params &P, cudaStream_t st) {
     if (n <= 0) return;
-    k_forces_mask<<<(n + 127) / 128, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, nb.fdat, dp, nb.mask, nb_count, key_s, cell_start,
+    (void)nb_count;
+    k_forces_mask<<<(n + 127) / 128, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, nb.fdat, dp, nb.mask, nb.words, key_s, cell_start,
                                                    acc, n, P);
 }
 
