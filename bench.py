@@ -39,6 +39,9 @@ WORKLOADS = {
     "dam_break_32K": ((1.14, 1.14, 1.14), 32500),
     "dam_break_16K": ((0.9, 0.9, 0.9), 16000),
 }
+# N > 1: the elongated tank of BASELINE configs[4], z-slabs of 400 cell layers (8,000,000 particles) per GPU;
+# at N = 8 this is exactly the 64,000,000-particle tank 4.56 x 4.56 x 146.23
+TANK_XY, TANK_Z_PER_GPU, TANK_PARTICLES_PER_GPU = 4.56, 146.23 / 8.0, 8000000
 
 
 def measured_peaks():
@@ -183,9 +186,17 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    workload = args.workload
-    box, _ = WORKLOADS[workload]
-    sim = gws.Simulator("cuda", box, device=local).setup_scene()
+    slab = world > 1
+    if slab:
+        workload = f"tank_{8 * world}M_slabs"
+        box = (TANK_XY, TANK_XY, TANK_Z_PER_GPU * world)
+        ident = [gws.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        sim = gws.Simulator("cuda", box, device=local).enable_slab(rank, world, ident[0]).setup_scene()
+    else:
+        workload = args.workload
+        box, _ = WORKLOADS[workload]
+        sim = gws.Simulator("cuda", box, device=local).setup_scene()
     ctx = sim.context()
     n = sim.n
     if args.neighbour_variant is not None:
@@ -195,7 +206,9 @@ def run_ours(args):
     sim.step_many(1, timed=False)
     sim.step_many(max(args.preroll - 1, 1), timed=False)
     ctx.synchronize()
-    ctx.set_option("flush_l2", 1 if args.flush_l2 else 0)
+    flush_l2 = args.flush_l2 and not slab  # a slab's working set (GBs) is far larger than L2 anyway
+    args.flush_l2 = flush_l2
+    ctx.set_option("flush_l2", 1 if flush_l2 else 0)
     sim.step_many(max(args.warmup, 3))
 
     # ---- timed region: exactly K steps, device time from CUDA events on the launching stream
@@ -206,16 +219,20 @@ def run_ours(args):
         dev_ms = sim.step_many(args.steps)
         barrier()
         wall = time.perf_counter() - wall0
-        if wall < 1.5:  # keep the GPU under the same load long enough for a few clock samples
+        launches = ctx.counter("kernel_launches") - launches0
+        if wall < 1.5 and not slab:  # keep the GPU under the same load long enough for a few clock samples
             ctx.set_option("flush_l2", 0)
             t_end = time.perf_counter() + 1.5
             while time.perf_counter() < t_end:
                 sim.step_many(50, timed=True)
             ctx.set_option("flush_l2", 1 if args.flush_l2 else 0)
-    launches = ctx.counter("kernel_launches") - launches0
     dev_ms = max_over_ranks(dev_ms)
-    total_particles = sum_over_ranks(float(n))
+    total_particles = sum_over_ranks(float(ctx.n if slab else n))
     value = total_particles * args.steps / (dev_ms * 1e-3)
+    if slab:
+        finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, dev_ms, wall, launches, total_particles,
+                    clocks, barrier, max_over_ranks)
+        return
 
     # ---- same loop with a warm L2 (no eviction), for information
     ctx.set_option("flush_l2", 0)
@@ -297,6 +314,49 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, dev_ms, wall, launches, total_particles,
+                clocks, barrier, max_over_ranks):
+    """N > 1: e2e (step + read-back of the owned particles every step), per-rank slab facts, the JSON line."""
+    peak, peak_src = measured_peaks()
+    sim.set_mirror_mode(1)
+    sim.step(2)
+    barrier()
+    t0 = time.perf_counter()
+    sim.step(args.e2e_steps)
+    barrier()
+    e2e_sec = max_over_ranks(time.perf_counter() - t0)
+    sim.set_mirror_mode(0)
+    info = ctx.slab_info()
+    infos = [None] * world
+    dist.all_gather_object(infos, info)
+    if rank == 0:
+        step_gbs = value / world * ALG_BYTES_PER_PARTICLE_STEP / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "particles": int(total_particles), "box": list(box),
+                       "preroll_steps": args.preroll,
+                       "parallelism": f"{world} z-slabs, ghost+migration exchange per step via ncclSend/ncclRecv",
+                       "slabs": [{k: i[k] for k in ("z0", "z1", "n_own", "mean_sent_per_step")} for i in infos],
+                       "l2": "no eviction: per-GPU working set (~2.5 GB) is far larger than the 126 MB L2"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": total_particles * args.e2e_steps / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": int(80 * total_particles), "steps": args.e2e_steps,
+                    "ms_per_step": 1e3 * e2e_sec / args.e2e_steps,
+                    "path": "CCUDAParticleSimulator::step() per rank, MirrorMode::Download (owned particles read back every step)"},
+            "gpu_launches": int(launches) * world,
+            "roofline": {"bound": "hbm", "kernel": "whole step (per GPU)", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": step_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "note": "step-level: 260 algorithmic B per particle-step (SURVEY.md §8d); per-kernel split is reported at N=1"},
+            "cpu_baseline": None,
+            "wall_ms_per_step": 1e3 * wall / args.steps,
+            "device": sim.device,
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
 
 
 def main():

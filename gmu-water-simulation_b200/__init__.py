@@ -16,6 +16,8 @@ from .binding import (  # noqa: F401
     SphContext,
     SphError,
     build,
+    comm_unique_id,
+    slab_plan,
     cuda_lib,
     declared_symbols,
     device_count,

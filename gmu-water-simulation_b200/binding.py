@@ -123,6 +123,10 @@ def cuda_lib():
             "sph_set_option": (i32, [vp, C.c_char_p, i32]),
             "sph_get_counter": (i32, [vp, C.c_char_p, P(u64)]),
             "sph_comm_unique_id": (i32, [vp]),
+            "sph_slab_plan": (i32, [i32, i32, i32, P(i32), P(i32)]),
+            "sph_slab_create": (i32, [P(SphConfig), P(vp)]),
+            "sph_slab_info": (i32, [vp, vp]),
+            "sph_download_owned": (i32, [vp, vp, u32, P(u32)]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)
@@ -144,6 +148,7 @@ def host_lib():
             "gmu_sim_create": (vp, [C.c_char_p, f, f, f, i32, i32]),
             "gmu_sim_destroy": (None, [vp]),
             "gmu_sim_last_error": (C.c_char_p, []),
+            "gmu_sim_enable_slab": (i32, [vp, i32, i32, vp]),
             "gmu_sim_setup_scene": (i32, [vp]),
             "gmu_sim_step": (i32, [vp, i32]),
             "gmu_sim_step_many": (i32, [vp, i32, C.POINTER(dbl)]),
@@ -189,6 +194,24 @@ def device_name(device=0):
     if rc:
         raise SphError(cuda_lib().sph_last_error(None).decode())
     return buf.value.decode()
+
+
+def comm_unique_id():
+    """128-byte NCCL id for slab mode (create on rank 0, broadcast to the other ranks)."""
+    buf = (C.c_uint8 * 128)()
+    rc = cuda_lib().sph_comm_unique_id(buf)
+    if rc:
+        raise SphError(cuda_lib().sph_last_error(None).decode())
+    return bytes(buf)
+
+
+def slab_plan(rz, world, rank):
+    """Owned z-layers [z0, z1) of `rank` (pure host logic, no device needed)."""
+    z0, z1 = C.c_int32(0), C.c_int32(0)
+    rc = cuda_lib().sph_slab_plan(int(rz), int(world), int(rank), C.byref(z0), C.byref(z1))
+    if rc:
+        raise SphError(cuda_lib().sph_last_error(None).decode())
+    return z0.value, z1.value
 
 
 def make_config(box, max_particles, device=0):
@@ -364,6 +387,22 @@ class SphContext:
     def set_option(self, name, value):
         self._ck(self.lib.sph_set_option(self._h, name.encode(), int(value)))
 
+    def download_owned(self):
+        """Owned particles in canonical order (slab mode: this rank's share; records carry the ids)."""
+        n = self.n
+        out = np.zeros(max(n, 1), dtype=PARTICLE_DTYPE)
+        got = C.c_uint32(0)
+        self._ck(self.lib.sph_download_owned(self._h, _ptr(out), out.shape[0], C.byref(got)))
+        return out[: got.value]
+
+    def slab_info(self):
+        out = np.zeros(8, dtype=np.int32)
+        rc = self.lib.sph_slab_info(self._h, _ptr(out))
+        if rc:
+            raise SphError("not a slab context")
+        keys = ("rank", "world", "z0", "z1", "z_base", "rz_local", "n_own", "mean_sent_per_step")
+        return dict(zip(keys, (int(v) for v in out)))
+
     def counter(self, name):
         v = C.c_uint64(0)
         rc = self.lib.sph_get_counter(self._h, name.encode(), C.byref(v))
@@ -409,6 +448,11 @@ class Simulator:
     def _ck(self, rc):
         if rc:
             raise SphError(self.lib.gmu_sim_last_error().decode())
+
+    def enable_slab(self, rank, world, nccl_id):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(nccl_id)[:128].ljust(128, b"\0"))
+        self._ck(self.lib.gmu_sim_enable_slab(self._h, int(rank), int(world), buf))
+        return self
 
     def setup_scene(self):
         self._ck(self.lib.gmu_sim_setup_scene(self._h))

@@ -32,7 +32,7 @@ void CBaseParticleSimulator::setupScene() {
     const unsigned int calculatedCount =
         (unsigned)(std::ceil(m_boxSize.z() / halfParticle) * std::ceil(m_boxSize.y() / halfParticle) *
                    std::ceil(m_boxSize.x() / 4 / halfParticle));
-    m_clParticles.reserve(calculatedCount);
+    if (reserveWholeScene()) m_clParticles.reserve(calculatedCount);
 
     if (m_scenario == DAM_BREAK) {
         const QVector3D offset = -m_boxSize / 2.0f;
@@ -40,16 +40,19 @@ void CBaseParticleSimulator::setupScene() {
             for (float x = 0; x < m_boxSize.x() / 4.0; x += halfParticle)
                 for (float z = 0; z < m_boxSize.z(); z += halfParticle)
                     addParticle(x + offset.x(), y + offset.y(), z + offset.z());
-        assert(calculatedCount == (unsigned)m_particlesCount);
-        m_maxParticlesCount = (cl_uint)m_particlesCount;
+        assert(calculatedCount == m_nextParticleId);
+        (void)calculatedCount;
+        m_maxParticlesCount = m_nextParticleId;
     } else {
         m_maxParticlesCount = calculatedCount;
     }
 }
 
 void CBaseParticleSimulator::addParticle(float x, float y, float z, cl_float3 initialVelocity) {
-    // :67-74 without the per-particle Qt3D entity
-    m_clParticles.emplace_back(x, y, z, (cl_uint)m_particlesCount, initialVelocity);
+    // :67-74 without the per-particle Qt3D entity; the id is the global running count
+    const cl_uint id = m_nextParticleId++;
+    if (!ownsParticle(x, y, z)) return;
+    m_clParticles.emplace_back(x, y, z, id, initialVelocity);
     m_particlesCount++;
 }
 
@@ -61,7 +64,7 @@ void CBaseParticleSimulator::generateParticles() {
     const QVector3D offset = -m_boxSize / 2.0f;
     const cl_float3 initialVelocity = {0.0f, m_boxSize.y() * 3.2f, 0.0f, 0.0f};
     for (int nozzle = 0; nozzle < m_emissionMultiplier; ++nozzle) {
-        if ((cl_uint)m_particlesCount >= (m_maxParticlesCount - (cl_uint)particlesPerIteration)) return;
+        if (m_nextParticleId >= (m_maxParticlesCount - (cl_uint)particlesPerIteration)) return;
         // one nozzle sits at the origin like the reference's; with more nozzles (extension) they form a
         // centred square array 3h apart so their particles never coincide
         const int side = (int)std::ceil(std::sqrt((double)m_emissionMultiplier));

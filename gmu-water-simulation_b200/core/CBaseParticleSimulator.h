@@ -103,6 +103,12 @@ protected:
     virtual double updateCollisions() = 0;
     virtual double integrate() = 0;
 
+    // Extension for the slab-decomposed simulator: scene generation walks the WHOLE scene (ids are the global
+    // running count, as in the reference) but only keeps the particles this instance owns.
+    virtual bool ownsParticle(float /*x*/, float /*y*/, float /*z*/) { return true; }
+    virtual bool reserveWholeScene() { return true; }
+    cl_uint m_nextParticleId = 0;  // global running count (== m_particlesCount unless the scene is filtered)
+
     bool isRunning() { return m_timer.isActive(); }
     void emitIterationChanged(unsigned long it) { for (auto &cb : m_iterationChanged) cb(it); }
     void emitErrorOccured(const char *what) { for (auto &cb : m_errorOccured) cb(what); }

@@ -2,6 +2,8 @@
 // C ABI, error propagation as in CGPUBaseParticleSimulator (src/CGPUBaseParticleSimulator.cpp:28-37).
 #include "CCUDAParticleSimulator.h"
 
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 
 static_assert(sizeof(CParticle::Physics) == sizeof(sph_particle), "host mirror record != ABI record");
@@ -21,12 +23,36 @@ void CCUDAParticleSimulator::setGravityVector(QVector3D newGravity) {
     if (m_cuda) m_cuda->check(sph_set_gravity(m_cuda->ctx(), gravity.x(), gravity.y(), gravity.z()), "setGravityVector");
 }
 
+void CCUDAParticleSimulator::enableSlab(int rank, int world, const unsigned char ncclId[128]) {
+    m_slab = true;
+    m_rank = rank;
+    m_world = world;
+    std::memcpy(m_ncclId, ncclId, 128);
+    if (sph_slab_plan(m_grid->zRes(), world, rank, &m_z0, &m_z1) != SPH_OK) throw CUDAException(sph_last_error(nullptr));
+}
+
+bool CCUDAParticleSimulator::ownsParticle(float, float, float z) {
+    if (!m_slab) return true;
+    // the z-layer exactly as updateGrid computes it (src/CCPUParticleSimulator.cpp:48,64-70)
+    int layer = (int)std::floor(((double)z + (double)m_boxSize.z() / 2.0) / (double)CParticle::h);
+    if (layer < 0) layer = 0;
+    else if (layer >= m_grid->zRes()) layer = m_grid->zRes() - 1;
+    return layer >= m_z0 && layer < m_z1;
+}
+
 void CCUDAParticleSimulator::setupScene() {
     CBaseParticleSimulator::setupScene();  // fills m_clParticles / m_maxParticlesCount
 
     // ≙ CGPUBaseParticleSimulator::setupKernels: size the device buffers, hand over walls and constants
+    // device capacity: the whole scene on one device; in slab mode the owned share plus room for the ghost
+    // layers and for load drifting between slabs
+    uint32_t capacity = m_maxParticlesCount > 0 ? m_maxParticlesCount : 1;
+    if (m_slab) {
+        const uint64_t face = (uint64_t)m_grid->xRes() * m_grid->yRes() * 4 * 48;
+        capacity = (uint32_t)std::min<uint64_t>((uint64_t)m_particlesCount * 13 / 10 + 2 * face + 1024, 0x7ffffff0u);
+    }
     sph_config cfg;
-    sph_config_init(&cfg, m_boxSize.x(), m_boxSize.y(), m_boxSize.z(), m_maxParticlesCount > 0 ? m_maxParticlesCount : 1);
+    sph_config_init(&cfg, m_boxSize.x(), m_boxSize.y(), m_boxSize.z(), capacity);
     cfg.grid_res[0] = m_grid->xRes();
     cfg.grid_res[1] = m_grid->yRes();
     cfg.grid_res[2] = m_grid->zRes();
@@ -38,10 +64,15 @@ void CCUDAParticleSimulator::setupScene() {
     cfg.wall_count = (int32_t)walls.size();
     std::memcpy(cfg.walls, walls.data(), walls.size() * sizeof(sWall));
     cfg.device = m_device;
-    m_cuda.reset(new CUDAWrapper(cfg));
+    if (m_slab) {
+        cfg.rank = m_rank;
+        cfg.world = m_world;
+        std::memcpy(cfg.nccl_id, m_ncclId, 128);
+    }
+    m_cuda.reset(new CUDAWrapper(cfg, m_slab));
 
     // page-lock the host mirror once: it never reallocates (reserved to the maximum count in setupScene)
-    if (m_clParticles.capacity() > 0)
+    if (!m_slab && m_clParticles.capacity() > 0)
         sph_pin_host_buffer(m_cuda->ctx(), m_clParticles.data(), m_clParticles.capacity() * sizeof(CParticle::Physics));
 
     m_deviceCount = 0;
@@ -60,6 +91,16 @@ void CCUDAParticleSimulator::pushNewParticles() {
 }
 
 void CCUDAParticleSimulator::step() {
+    if (m_slab) {  // slab mode: the exchange is part of the fused device step
+        try {
+            m_cuda->check(sph_step(m_cuda->ctx(), 1, nullptr), "step");
+            if (m_mirrorMode != Resident) syncHostMirror();
+        } catch (CUDAException &exc) {
+            emitErrorOccured(exc.what());
+            stop();
+        }
+        return;
+    }
     try {
         if (m_mirrorMode == RoundTrip && m_cuda) {
             m_cuda->check(sph_upload_particles(m_cuda->ctx(), reinterpret_cast<const sph_particle *>(m_clParticles.data()),
@@ -75,7 +116,7 @@ void CCUDAParticleSimulator::step() {
 
 void CCUDAParticleSimulator::stepMany(int steps, double *deviceMs) {
     if (!m_cuda) throw CUDAException("stepMany before setupScene");
-    if (m_scenario == FOUNTAIN || m_brute) {  // emission / all-pairs go through the phase path
+    if ((m_scenario == FOUNTAIN || m_brute) && !m_slab) {  // emission / all-pairs go through the phase path
         for (int k = 0; k < steps; ++k) { CBaseParticleSimulator::step(); addIterations(1); }
         if (deviceMs) { m_cuda->check(sph_synchronize(m_cuda->ctx()), "stepMany"); *deviceMs = 0.0; }
         return;
@@ -86,6 +127,13 @@ void CCUDAParticleSimulator::stepMany(int steps, double *deviceMs) {
 
 void CCUDAParticleSimulator::syncHostMirror() {
     uint32_t n = 0;
+    if (m_slab) {  // owned particles only, compact, canonical order
+        sph_particle_count(m_cuda->ctx(), &n);
+        m_clParticles.resize(n, CParticle::Physics(0, 0, 0, 0));
+        m_particlesCount = (cl_int)n;
+        m_cuda->check(sph_download_owned(m_cuda->ctx(), reinterpret_cast<sph_particle *>(m_clParticles.data()), n, &n), "syncHostMirror");
+        return;
+    }
     m_cuda->check(sph_download_particles(m_cuda->ctx(), reinterpret_cast<sph_particle *>(m_clParticles.data()),
                                          (uint32_t)m_clParticles.size(), &n), "syncHostMirror");
 }

@@ -37,6 +37,12 @@ public:
     void syncHostMirror();                                 // device -> m_clParticles (indexed by id)
     void setMirrorMode(MirrorMode m) { m_mirrorMode = m; }
     void setBruteForce(bool on) { m_brute = on; }          // CGPUBruteParticleSimulator semantics (all pairs)
+    // Multi-GPU extension: make this instance rank `rank` of `world` z-slabs (call before setupScene).  ncclId is
+    // the 128-byte id from sph_comm_unique_id(), identical on all ranks.  In slab mode the host mirror holds this
+    // rank's owned particles only (compact, ids in the records) and step() runs the fused device step.
+    void enableSlab(int rank, int world, const unsigned char ncclId[128]);
+    bool slabMode() const { return m_world > 1 || m_slab; }
+    void slabRange(int &z0, int &z1) const { z0 = m_z0; z1 = m_z1; }
     sph_context *context() const { return m_cuda ? m_cuda->ctx() : nullptr; }
 
 protected:
@@ -46,8 +52,15 @@ protected:
     double updateCollisions() override;
     double integrate() override;
 
+    bool ownsParticle(float x, float y, float z) override;
+    bool reserveWholeScene() override { return !m_slab; }
+
 private:
     void pushNewParticles();
+
+    bool m_slab = false;
+    int m_rank = 0, m_world = 1, m_z0 = 0, m_z1 = 0;
+    unsigned char m_ncclId[128] = {0};
 
     int m_device;
     std::unique_ptr<CUDAWrapper> m_cuda;

@@ -37,8 +37,9 @@ public:
 
 class CUDAWrapper {
 public:
-    explicit CUDAWrapper(const sph_config &cfg) {
-        if (sph_create(&cfg, &m_ctx) != SPH_OK) throw CUDAException(sph_last_error(nullptr));
+    explicit CUDAWrapper(const sph_config &cfg, bool slab = false) {
+        const int rc = slab ? sph_slab_create(&cfg, &m_ctx) : sph_create(&cfg, &m_ctx);
+        if (rc != SPH_OK) throw CUDAException(sph_last_error(nullptr));
     }
     ~CUDAWrapper() { sph_destroy(m_ctx); }
     CUDAWrapper(const CUDAWrapper &) = delete;

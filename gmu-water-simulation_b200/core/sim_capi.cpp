@@ -104,6 +104,13 @@ int gmu_sim_emit(gmu_sim *s, int n_steps) {
     return guarded([&] { for (int k = 0; k < n_steps; ++k) H(s)->sim->doWork(); });
 }
 
+int gmu_sim_enable_slab(gmu_sim *s, int rank, int world, const unsigned char *nccl_id128) {
+    return guarded([&] {
+        if (!H(s)->cuda) throw std::runtime_error("gmu_sim_enable_slab: not a CUDA simulator");
+        H(s)->cuda->enableSlab(rank, world, nccl_id128);
+    });
+}
+
 int gmu_sim_set_mirror_mode(gmu_sim *s, int mode) {
     return guarded([&] {
         if (!H(s)->cuda) throw std::runtime_error("gmu_sim_set_mirror_mode: not a CUDA simulator");

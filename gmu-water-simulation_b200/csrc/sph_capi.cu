@@ -11,6 +11,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is resolved lazily with dlopen (slab mode), never linked
+
 #include "sph_kernels.h"
 
 using namespace sph;
@@ -58,6 +61,23 @@ struct sph_context {
     float4 *d_flush = nullptr;
     size_t flush_count = 0;
     std::vector<cudaEvent_t> step_events;
+    // slab mode (multi-GPU): this rank's z-range, exchange buffers and NCCL communicator
+    struct Slab *slab = nullptr;
+    uint32_t in_off = 0;  // the next grid build reads A[in_off, in_off + n)
+};
+
+// One rank of a 1-D slab decomposition along z (the slowest cell axis, so a slab is a contiguous key range
+// and, after the sort, a contiguous particle range).
+struct Slab {
+    int rank = 0, world = 1;
+    int z0 = 0, z1 = 0;        // owned global layers [z0, z1)
+    int z_base = 0, rz_local = 0;
+    uint32_t n_own = 0;        // owned particles: A[in_off, in_off + n_own)
+    int cap_face = 0;          // capacity (particles) of each face buffer
+    float4 *down_pos = nullptr, *down_vel = nullptr, *up_pos = nullptr, *up_vel = nullptr;
+    int *d_counters = nullptr;  // [0] to lower, [1] to upper, [2] from lower, [3] from upper
+    ncclComm_t comm = nullptr;
+    uint64_t sent_particles = 0, exchanges = 0;
 };
 
 namespace {
@@ -93,6 +113,8 @@ Params make_params(const sph_config &c) {
     P.ry = c.grid_res[1];
     P.rz = c.grid_res[2];
     P.n_cells = P.rx * P.ry * P.rz;
+    P.rz_global = P.rz;
+    P.z_base = 0;
     // src/CCPUParticleSimulator.cpp:46-48: m_boxSize.x() / 2.0 and CParticle::h widen to double
     P.hbx = (double)c.box[0] / 2.0;
     P.hby = (double)c.box[1] / 2.0;
@@ -155,10 +177,11 @@ struct PhaseTimer {
 // ---- the pipeline pieces (enqueue only) -------------------------------------------------------
 void enqueue_grid(sph_context *c) {
     const int n = (int)c->n;
-    launch_cell_key_hist(c->pos_a, n, c->g, c->P, c->stream);
+    const float4 *pa = c->pos_a + c->in_off, *va = c->vel_a + c->in_off;
+    launch_cell_key_hist(pa, n, c->g, c->P, c->stream);
     launch_scan(c->g, c->stream);
-    launch_bucket(c->pos_a, n, c->g, c->stream);
-    launch_rank_scatter(c->pos_a, c->vel_a, c->pos_s, c->vel_s, n, c->g, c->nb, c->stream);
+    launch_bucket(pa, n, c->g, c->stream);
+    launch_rank_scatter(pa, va, c->pos_s, c->vel_s, n, c->g, c->nb, c->stream);
     c->kernel_launches += 4;
 }
 // variant 1 (default): bitmask passes of sph_neighbours_v2.cu; variant 0: the plain float4 walk of
@@ -181,6 +204,7 @@ void enqueue_forces(sph_context *c) {
 void enqueue_integrate(sph_context *c) {
     launch_integrate_collide(c->pos_s, c->vel_s, c->acc, c->pos_a, c->vel_a, (int)c->n, c->P, c->stream);
     c->kernel_launches += 1;
+    c->in_off = 0;  // integrate writes A[0, n) in canonical order
 }
 void enqueue_step(sph_context *c) {
     enqueue_grid(c);
@@ -202,6 +226,158 @@ void drop_graph(sph_context *c) {
 const float4 *view_pos(const sph_context *c) { return c->a_aligned || !c->s_valid ? c->pos_a : c->pos_s; }
 const float4 *view_vel(const sph_context *c) { return c->a_aligned || !c->s_valid ? c->vel_a : c->vel_s; }
 bool aux_aligned(const sph_context *c) { return c->s_valid; }  // dp/acc/key_s index == view index
+
+// ---------------------------------------------------------------- slab mode (multi-GPU) ----------
+// NCCL is resolved at run time (dlopen) so that the single-GPU library has no link dependency and, in
+// a process that already carries torch's bundled NCCL, the very same copy is used.
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi *nccl_api(std::string *why) {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (api.handle) {
+            auto sym = [&](const char *n) { return dlsym(api.handle, n); };
+            api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+            api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+            api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+            api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+            api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+            api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+            api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+            api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+        }
+    }
+    const bool ok = api.handle && api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv &&
+                    api.GroupStart && api.GroupEnd && api.GetErrorString;
+    if (!ok && why) *why = "NCCL::libnccl.so.2 could not be loaded (slab mode needs NCCL)";
+    return ok ? &api : nullptr;
+}
+
+#define NCCL_TRY(ctx, api, call)                                                                          \
+    do {                                                                                                  \
+        ncclResult_t r_ = (call);                                                                         \
+        if (r_ != ncclSuccess)                                                                            \
+            return fail(ctx, SPH_ERR_COMM, std::string("NCCL::") + (api)->GetErrorString(r_) + " | " #call); \
+    } while (0)
+
+void slab_release(sph_context *c) {
+    Slab *s = c->slab;
+    if (!s) return;
+    if (s->comm) {
+        if (NcclApi *api = nccl_api(nullptr)) api->CommDestroy(s->comm);
+    }
+    for (void *p : {(void *)s->down_pos, (void *)s->down_vel, (void *)s->up_pos, (void *)s->up_vel, (void *)s->d_counters})
+        if (p) cudaFree(p);
+    delete s;
+    c->slab = nullptr;
+}
+
+// Layers [z0, z1) of rank `rank`: equal split, the remainder goes to the lowest ranks.
+void slab_plan(int rz, int world, int rank, int *z0, int *z1) {
+    const int base = rz / world, extra = rz % world;
+    *z0 = rank * base + std::min(rank, extra);
+    *z1 = *z0 + base + (rank < extra ? 1 : 0);
+}
+
+// Ghost exchange + migration in one message pair per face.  Every rank sends, to each neighbour, its
+// particles lying in the two layers on either side of the shared face (ghosts for the neighbour) or beyond
+// it (migrants); the receiver appends them behind its own particles and the ordinary grid build sorts all.
+int slab_exchange(sph_context *c) {
+    Slab &s = *c->slab;
+    NcclApi *api = nccl_api(&c->err);
+    if (!api) return SPH_ERR_COMM;
+    const bool has_down = s.rank > 0, has_up = s.rank + 1 < s.world;
+    float4 *pa = c->pos_a + c->in_off, *va = c->vel_a + c->in_off;
+    CUDA_TRY(c, cudaMemsetAsync(s.d_counters, 0, 4 * sizeof(int), c->stream));
+    launch_slab_pack(pa, va, (int)s.n_own, has_down ? s.z0 + 2 : -1, has_up ? s.z1 - 2 : 0x7fffffff, s.down_pos, s.down_vel,
+                     s.up_pos, s.up_vel, s.d_counters, s.cap_face, c->P, c->stream);
+    c->kernel_launches += 1;
+    // the counts travel first (4-byte messages), then the payloads with their exact sizes
+    NCCL_TRY(c, api, api->GroupStart());
+    if (has_down) {
+        NCCL_TRY(c, api, api->Send(s.d_counters + 0, 1, ncclInt32, s.rank - 1, s.comm, c->stream));
+        NCCL_TRY(c, api, api->Recv(s.d_counters + 2, 1, ncclInt32, s.rank - 1, s.comm, c->stream));
+    }
+    if (has_up) {
+        NCCL_TRY(c, api, api->Send(s.d_counters + 1, 1, ncclInt32, s.rank + 1, s.comm, c->stream));
+        NCCL_TRY(c, api, api->Recv(s.d_counters + 3, 1, ncclInt32, s.rank + 1, s.comm, c->stream));
+    }
+    NCCL_TRY(c, api, api->GroupEnd());
+    int h[4] = {0, 0, 0, 0};
+    CUDA_TRY(c, cudaMemcpyAsync(h, s.d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    const int send_down = h[0], send_up = h[1], recv_down = has_down ? h[2] : 0, recv_up = has_up ? h[3] : 0;
+    REQUIRE(c, send_down <= s.cap_face && send_up <= s.cap_face, SPH_ERR_STATE, "slab: face buffer overflow");
+    REQUIRE(c, (uint64_t)c->in_off + s.n_own + (uint64_t)recv_down + (uint64_t)recv_up <= c->cap, SPH_ERR_STATE,
+            "slab: local particle capacity exceeded");
+    float4 *rp = pa + s.n_own, *rv = va + s.n_own;
+    NCCL_TRY(c, api, api->GroupStart());
+    if (has_down) {
+        if (send_down) {
+            NCCL_TRY(c, api, api->Send(s.down_pos, (size_t)send_down * 4, ncclFloat32, s.rank - 1, s.comm, c->stream));
+            NCCL_TRY(c, api, api->Send(s.down_vel, (size_t)send_down * 4, ncclFloat32, s.rank - 1, s.comm, c->stream));
+        }
+        if (recv_down) {
+            NCCL_TRY(c, api, api->Recv(rp, (size_t)recv_down * 4, ncclFloat32, s.rank - 1, s.comm, c->stream));
+            NCCL_TRY(c, api, api->Recv(rv, (size_t)recv_down * 4, ncclFloat32, s.rank - 1, s.comm, c->stream));
+        }
+    }
+    if (has_up) {
+        if (send_up) {
+            NCCL_TRY(c, api, api->Send(s.up_pos, (size_t)send_up * 4, ncclFloat32, s.rank + 1, s.comm, c->stream));
+            NCCL_TRY(c, api, api->Send(s.up_vel, (size_t)send_up * 4, ncclFloat32, s.rank + 1, s.comm, c->stream));
+        }
+        if (recv_up) {
+            NCCL_TRY(c, api, api->Recv(rp + recv_down, (size_t)recv_up * 4, ncclFloat32, s.rank + 1, s.comm, c->stream));
+            NCCL_TRY(c, api, api->Recv(rv + recv_down, (size_t)recv_up * 4, ncclFloat32, s.rank + 1, s.comm, c->stream));
+        }
+    }
+    NCCL_TRY(c, api, api->GroupEnd());
+    c->n = s.n_own + (uint32_t)recv_down + (uint32_t)recv_up;
+    s.sent_particles += (uint64_t)send_down + (uint64_t)send_up;
+    s.exchanges += 1;
+    return SPH_OK;
+}
+
+int slab_step(sph_context *c, int n_steps, double *ms) {
+    Slab &s = *c->slab;
+    PhaseTimer t(c, ms);
+    for (int k = 0; k < n_steps; ++k) {
+        int rc = slab_exchange(c);
+        if (rc) return rc;
+        enqueue_step(c);
+        // the owned particles are the contiguous run of the owned layers in the canonical order
+        const size_t rxy = (size_t)c->P.rx * c->P.ry;
+        int lo = 0, hi = 0;
+        CUDA_TRY(c, cudaMemcpyAsync(&lo, c->g.cell_start + (size_t)(s.z0 - s.z_base) * rxy, sizeof(int),
+                                    cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(&hi, c->g.cell_start + (size_t)(s.z1 - s.z_base) * rxy, sizeof(int),
+                                    cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        c->in_off = (uint32_t)lo;
+        s.n_own = (uint32_t)(hi - lo);
+    }
+    c->steps += (uint64_t)n_steps;
+    c->s_valid = c->grid_valid = c->density_valid = c->forces_valid = c->a_aligned = true;
+    int rc = check_launch(c, "slab step");
+    return rc ? rc : t.finish();
+}
 
 }  // namespace
 
@@ -268,6 +444,7 @@ int sph_destroy(sph_context *c) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->d_flush) cudaFree(c->d_flush);
+    slab_release(c);
     for (cudaEvent_t e : c->step_events) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -376,12 +553,15 @@ int sph_upload_particles(sph_context *c, const sph_particle *aos, uint32_t n) {
     REQUIRE(c, aos || n == 0, SPH_ERR_ARGUMENT, "sph_upload_particles: NULL particles");
     CUDA_TRY(c, cudaSetDevice(c->device));
     c->n = n;
+    c->in_off = 0;
+    if (c->slab) c->slab->n_own = n;
     c->s_valid = c->grid_valid = c->a_aligned = c->density_valid = c->forces_valid = false;
     return upload_range(c, aos, 0, n);
 }
 
 int sph_append_particles(sph_context *c, const sph_particle *aos, uint32_t n_new) {
     REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    REQUIRE(c, !c->slab, SPH_ERR_STATE, "sph_append_particles: not available in slab mode");
     REQUIRE(c, (uint64_t)c->n + n_new <= c->cap, SPH_ERR_ARGUMENT, "sph_append_particles: exceeds max_particles");
     REQUIRE(c, aos || n_new == 0, SPH_ERR_ARGUMENT, "sph_append_particles: NULL particles");
     CUDA_TRY(c, cudaSetDevice(c->device));
@@ -414,7 +594,7 @@ int sph_download_particles(sph_context *c, sph_particle *aos, uint32_t capacity,
 
 int sph_particle_count(const sph_context *c, uint32_t *n_out) {
     if (!c || !n_out) return SPH_ERR_ARGUMENT;
-    *n_out = c->n;
+    *n_out = c->slab ? c->slab->n_own : c->n;
     return SPH_OK;
 }
 
@@ -494,6 +674,7 @@ int sph_step(sph_context *c, int n_steps, double *ms) {
     REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
     REQUIRE(c, n_steps >= 0, SPH_ERR_ARGUMENT, "sph_step: negative step count");
     CUDA_TRY(c, cudaSetDevice(c->device));
+    if (c->slab) return slab_step(c, n_steps, ms);
     if (n_steps == 0 || c->n == 0) {
         if (ms) *ms = 0.0;
         return SPH_OK;
@@ -713,17 +894,27 @@ int sph_brute_neighbour_counts(sph_context *c, int32_t *counts) {
 int sph_stats(sph_context *c, double *out6) {
     REQUIRE(c, c && out6, SPH_ERR_ARGUMENT, "sph_stats: NULL argument");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    launch_stats(view_pos(c), view_vel(c), (int)c->n, c->d_stats, c->stream);
+    const size_t so = c->slab ? c->in_off : 0;
+    const uint32_t sn = c->slab ? c->slab->n_own : c->n;
+    launch_stats(view_pos(c) + so, view_vel(c) + so, (int)sn, c->d_stats, c->stream);
     c->kernel_launches += 1;
     double h[8];
     CUDA_TRY(c, cudaMemcpyAsync(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    const double n = (double)c->n;
+    const double n = (double)sn;
     unsigned bits;
     std::memcpy(&bits, &h[5], sizeof(bits));
     bits = (bits & 0x80000000u) ? (bits & 0x7fffffffu) : ~bits;
     float ymax;
     std::memcpy(&ymax, &bits, sizeof(ymax));
+    if (c->slab) {
+        // partial sums of this rank: the caller adds them over ranks (and takes the max of out6[4])
+        out6[0] = 0.5 * (double)c->P.mass * h[0];
+        out6[1] = h[1]; out6[2] = h[2]; out6[3] = h[3];
+        out6[4] = n > 0 ? (double)ymax + (double)c->cfg.box[1] / 2.0 : 0;
+        out6[5] = h[4];
+        return check_launch(c, "stats");
+    }
     out6[0] = 0.5 * (double)c->P.mass * h[0];
     out6[1] = n > 0 ? h[1] / n : 0;
     out6[2] = n > 0 ? h[2] / n : 0;
@@ -757,8 +948,121 @@ int sph_get_counter(const sph_context *c, const char *name, uint64_t *value) {
 }
 
 int sph_comm_unique_id(uint8_t out[128]) {
-    (void)out;
-    return fail(nullptr, SPH_ERR_COMM, "sph_comm_unique_id: slab mode not built into this library yet");
+    REQUIRE(nullptr, out, SPH_ERR_ARGUMENT, "sph_comm_unique_id: NULL buffer");
+    std::string why;
+    NcclApi *api = nccl_api(&why);
+    if (!api) return fail(nullptr, SPH_ERR_COMM, why);
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    ncclUniqueId id;
+    NCCL_TRY(nullptr, api, api->GetUniqueId(&id));
+    std::memcpy(out, &id, 128);
+    return SPH_OK;
+}
+
+int sph_slab_plan(int32_t rz, int32_t world, int32_t rank, int32_t *z0, int32_t *z1) {
+    REQUIRE(nullptr, z0 && z1 && world >= 1 && rank >= 0 && rank < world, SPH_ERR_ARGUMENT, "sph_slab_plan: bad argument");
+    REQUIRE(nullptr, rz / world >= 4, SPH_ERR_ARGUMENT, "sph_slab_plan: every slab needs at least 4 z-layers");
+    int a, b;
+    slab_plan(rz, world, rank, &a, &b);
+    *z0 = a;
+    *z1 = b;
+    return SPH_OK;
+}
+
+int sph_slab_create(const sph_config *cfg, sph_context **out) {
+    REQUIRE(nullptr, cfg && out, SPH_ERR_ARGUMENT, "sph_slab_create: NULL argument");
+    *out = nullptr;
+    REQUIRE(nullptr, cfg->world >= 1 && cfg->rank >= 0 && cfg->rank < cfg->world, SPH_ERR_ARGUMENT, "sph_slab_create: bad rank/world");
+    REQUIRE(nullptr, cfg->grid_res[2] / cfg->world >= 4, SPH_ERR_ARGUMENT, "sph_slab_create: every slab needs at least 4 z-layers");
+    int z0, z1;
+    slab_plan(cfg->grid_res[2], cfg->world, cfg->rank, &z0, &z1);
+    const int z_base = std::max(z0 - 2, 0), z_top = std::min(z1 + 2, cfg->grid_res[2]);
+    sph_config local = *cfg;
+    local.grid_res[2] = z_top - z_base;  // owned layers + two ghost layers per interior face
+    local.world = 1;
+    int rc = sph_create(&local, out);
+    if (rc) return rc;
+    sph_context *c = *out;
+    c->cfg = *cfg;
+    c->P.rz_global = cfg->grid_res[2];
+    c->P.z_base = z_base;
+    c->opt_use_graph = 0;  // the particle count changes every step
+    Slab *s = new Slab();
+    c->slab = s;
+    s->rank = cfg->rank;
+    s->world = cfg->world;
+    s->z0 = z0;
+    s->z1 = z1;
+    s->z_base = z_base;
+    s->rz_local = z_top - z_base;
+    // face buffers: up to 4 layers (2 ghost + 2 of slack for migrants) at 48 particles per cell
+    const size_t face = (size_t)cfg->grid_res[0] * cfg->grid_res[1] * 4 * 48;
+    s->cap_face = (int)std::min<size_t>(face, c->cap);
+#define SLAB_TRY(call)                                                             \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) {                                                   \
+            std::string m = std::string("CUDA::") + cudaGetErrorName(e_) + " | " #call; \
+            sph_destroy(c);                                                        \
+            *out = nullptr;                                                        \
+            return fail(nullptr, SPH_ERR_CUDA, m);                                 \
+        }                                                                          \
+    } while (0)
+    SLAB_TRY(dalloc(&s->down_pos, (size_t)s->cap_face));
+    SLAB_TRY(dalloc(&s->down_vel, (size_t)s->cap_face));
+    SLAB_TRY(dalloc(&s->up_pos, (size_t)s->cap_face));
+    SLAB_TRY(dalloc(&s->up_vel, (size_t)s->cap_face));
+    SLAB_TRY(dalloc(&s->d_counters, (size_t)4));
+#undef SLAB_TRY
+    if (cfg->world > 1) {
+        std::string why;
+        NcclApi *api = nccl_api(&why);
+        if (!api) {
+            sph_destroy(c);
+            *out = nullptr;
+            return fail(nullptr, SPH_ERR_COMM, why);
+        }
+        ncclUniqueId id;
+        std::memcpy(&id, cfg->nccl_id, 128);
+        ncclResult_t r = api->CommInitRank(&s->comm, cfg->world, id, cfg->rank);
+        if (r != ncclSuccess) {
+            std::string m = std::string("NCCL::") + api->GetErrorString(r) + " | ncclCommInitRank";
+            sph_destroy(c);
+            *out = nullptr;
+            return fail(nullptr, SPH_ERR_COMM, m);
+        }
+    }
+    return SPH_OK;
+}
+
+int sph_slab_info(const sph_context *c, int32_t out8[8]) {
+    if (!c || !out8 || !c->slab) return SPH_ERR_ARGUMENT;
+    const Slab &s = *c->slab;
+    out8[0] = s.rank; out8[1] = s.world; out8[2] = s.z0; out8[3] = s.z1; out8[4] = s.z_base; out8[5] = s.rz_local;
+    out8[6] = (int32_t)s.n_own; out8[7] = (int32_t)(s.exchanges ? s.sent_particles / s.exchanges : 0);
+    return SPH_OK;
+}
+
+int sph_download_owned(sph_context *c, sph_particle *aos, uint32_t capacity, uint32_t *n_out) {
+    REQUIRE(c, c && aos, SPH_ERR_ARGUMENT, "sph_download_owned: NULL argument");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const uint32_t n = c->slab ? c->slab->n_own : c->n, off = c->slab ? c->in_off : 0;
+    REQUIRE(c, capacity >= n, SPH_ERR_ARGUMENT, "sph_download_owned: buffer too small");
+    const bool aux = aux_aligned(c) && c->a_aligned;  // aux arrays share A's order after a full step
+    for (uint32_t base = 0; base < n;) {
+        const uint32_t chunk = (uint32_t)std::min<size_t>(n - base, c->stage_cap);
+        const size_t o = (size_t)off + base;
+        launch_soa_to_aos((c->a_aligned || !c->s_valid ? c->pos_a : c->pos_s) + o, (c->a_aligned || !c->s_valid ? c->vel_a : c->vel_s) + o,
+                          aux ? c->acc + o : nullptr, aux ? c->dp + o : nullptr, aux ? c->g.key_s + o : nullptr, c->d_stage,
+                          -1, (int)chunk, (int)chunk, c->P, c->stream);
+        c->kernel_launches += 1;
+        CUDA_TRY(c, cudaMemcpyAsync(aos + base, c->d_stage, (size_t)chunk * sizeof(sph_particle), cudaMemcpyDeviceToHost,
+                                    c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        base += chunk;
+    }
+    if (n_out) *n_out = n;
+    return check_launch(c, "download_owned");
 }
 
 }  // extern "C"

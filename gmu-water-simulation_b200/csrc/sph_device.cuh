@@ -21,6 +21,8 @@ struct WallDev {
 struct Params {
     int rx, ry, rz;       // grid resolution (x fastest, z slowest: include/CGrid.h:27)
     int n_cells;          // rx*ry*rz
+    int rz_global;        // z resolution of the whole tank (== rz on a single device)
+    int z_base;           // slab mode: global index of local z-layer 0 (0 on a single device)
     double hbx, hby, hbz; // double(box)/2.0           (src/CCPUParticleSimulator.cpp:46-48)
     double h_d;           // double(h)
     float h, h2;          // h2 = fl32(h*h) == 0x3b08df0c
@@ -53,7 +55,9 @@ __device__ __forceinline__ int cell_coord(float x, double half_box, double h_d, 
 __device__ __forceinline__ int cell_key(float4 p, const Params &P) {
     int cx = cell_coord(p.x, P.hbx, P.h_d, P.rx);
     int cy = cell_coord(p.y, P.hby, P.h_d, P.ry);
-    int cz = cell_coord(p.z, P.hbz, P.h_d, P.rz);
+    // slab mode: the global layer (clamped like the reference clamps it) is shifted into the local grid
+    int cz = cell_coord(p.z, P.hbz, P.h_d, P.rz_global) - P.z_base;
+    cz = min(max(cz, 0), P.rz - 1);
     return cx + cy * P.rx + cz * P.rx * P.ry;
 }
 

@@ -63,8 +63,14 @@ struct ParticleAoS {  // == sph_particle
     unsigned id, cell_id;
 };
 void launch_aos_to_soa(const ParticleAoS *aos, float4 *pos, float4 *vel, int n, cudaStream_t st);
+// id_base >= 0: record of particle `id` goes to aos[id - id_base] (ids outside [id_base, id_base+id_count) are skipped);
+// id_base < 0 : compact mode, particle at index i goes to aos[i] (slab mode: owned sub-range, order = canonical order)
 void launch_soa_to_aos(const float4 *pos, const float4 *vel, const float4 *acc, const float4 *dp, const int *key,
                        ParticleAoS *aos_by_id, int id_base, int id_count, int n, const Params &P, cudaStream_t st);
+// slab mode: append the owned particles lying in the 2+2 layers around each face to the send buffers
+void launch_slab_pack(const float4 *pos, const float4 *vel, int n, int z_lo_below, int z_hi_from, float4 *down_pos,
+                      float4 *down_vel, float4 *up_pos, float4 *up_vel, int *counters, int cap_face, const Params &P,
+                      cudaStream_t st);
 void launch_scatter_by_id_i32(const float4 *pos, const int *src, int *dst_by_id, int n, cudaStream_t st);
 void launch_scatter_dpa_by_id(const float4 *pos, const float4 *dp, const float4 *acc, float *rho, float *p, float *acc3,
                               int n, cudaStream_t st);

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) k_soa_to_aos(const float4 *__restrict__ p
     if (i >= n) return;
     const float4 p = __ldg(pos + i);
     const int id = __float_as_int(p.w);
-    const int slot = id - id_base;
+    const int slot = id_base < 0 ? i : id - id_base;
     if (slot < 0 || slot >= id_count) return;
     const float4 v = __ldg(vel + i);
     const float4 a = acc ? __ldg(acc + i) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -43,12 +43,13 @@ __global__ void __launch_bounds__(256) k_soa_to_aos(const float4 *__restrict__ p
     const int k = key ? __ldg(key + i) : 0;
     const int rxy = P.rx * P.ry;
     const int cz = k / rxy, cy = (k - cz * rxy) / P.rx, cx = k - cz * rxy - cy * P.rx;
+    const int cz_global = cz + P.z_base, k_global = k + P.z_base * rxy;  // slab mode reports global cells
     float4 *rec = reinterpret_cast<float4 *>(out + slot);
     rec[0] = make_float4(p.x, p.y, p.z, 0.0f);
     rec[1] = make_float4(v.x, v.y, v.z, 0.0f);
     rec[2] = make_float4(a.x, a.y, a.z, 0.0f);
-    rec[3] = make_float4(__int_as_float(cx), __int_as_float(cy), __int_as_float(cz), 0.0f);
-    rec[4] = make_float4(d.x, d.y, p.w, __int_as_float(k));
+    rec[3] = make_float4(__int_as_float(cx), __int_as_float(cy), __int_as_float(cz_global), 0.0f);
+    rec[4] = make_float4(d.x, d.y, p.w, __int_as_float(k_global));
 }
 
 void launch_soa_to_aos(const float4 *pos, const float4 *vel, const float4 *acc, const float4 *dp, const int *key,
@@ -213,6 +214,42 @@ void launch_brute_forces(const float4 *pos, const float4 *vel, const float4 *dp,
                          cudaStream_t st) {
     if (n <= 0) return;
     k_brute_forces<256><<<(n + 255) / 256, 256, 0, st>>>(pos, vel, dp, acc, n, P);
+}
+
+// ================================================================= slab mode: face packing
+// A particle whose (global, clamped) z-layer is below z_lo_below goes to the lower neighbour, one at or
+// above z_hi_from to the upper neighbour: that is the neighbour's two ghost layers plus everything that
+// has migrated out of this slab.  Arrival order in the buffers is arbitrary; the receiver sorts.
+__global__ void __launch_bounds__(256) k_slab_pack(const float4 *__restrict__ pos, const float4 *__restrict__ vel, int n,
+                                                   int z_lo_below, int z_hi_from, float4 *__restrict__ down_pos,
+                                                   float4 *__restrict__ down_vel, float4 *__restrict__ up_pos,
+                                                   float4 *__restrict__ up_vel, int *__restrict__ counters, int cap_face,
+                                                   const __grid_constant__ Params P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = __ldg(pos + i);
+    const int cz = cell_coord(p.z, P.hbz, P.h_d, P.rz_global);
+    if (cz < z_lo_below) {
+        const int s = atomicAdd(counters + 0, 1);
+        if (s < cap_face) {
+            down_pos[s] = p;
+            down_vel[s] = __ldg(vel + i);
+        }
+    }
+    if (cz >= z_hi_from) {
+        const int s = atomicAdd(counters + 1, 1);
+        if (s < cap_face) {
+            up_pos[s] = p;
+            up_vel[s] = __ldg(vel + i);
+        }
+    }
+}
+void launch_slab_pack(const float4 *pos, const float4 *vel, int n, int z_lo_below, int z_hi_from, float4 *down_pos,
+                      float4 *down_vel, float4 *up_pos, float4 *up_vel, int *counters, int cap_face, const Params &P,
+                      cudaStream_t st) {
+    if (n <= 0) return;
+    k_slab_pack<<<(n + 255) / 256, 256, 0, st>>>(pos, vel, n, z_lo_below, z_hi_from, down_pos, down_vel, up_pos, up_vel,
+                                                 counters, cap_face, P);
 }
 
 // ================================================================= L2 eviction for benchmarking

@@ -147,8 +147,18 @@ int sph_stats(sph_context *ctx, double *out6);
 int sph_set_option(sph_context *ctx, const char *name, int value);
 int sph_get_counter(const sph_context *ctx, const char *name, uint64_t *value); /* "kernel_launches", "graph_launches", "steps" */
 
-/* ---- slab mode plumbing: rank 0 creates the id, the launcher broadcasts it (torch.distributed / file) ---- */
+/* ---- slab mode (multi-GPU extension; the reference is single-device): 1-D decomposition along z, the slowest
+ * cell axis of CGrid::at (include/CGrid.h:27).  One process per GPU; rank 0 creates the NCCL id and the launcher
+ * broadcasts it (torch.distributed / MPI / a file).  cfg describes the WHOLE tank (box, grid_res) plus rank, world,
+ * nccl_id; max_particles is this rank's capacity (owned + ghost particles).  Every step exchanges, per face, the
+ * two boundary layers (ghosts) and the particles that crossed the face (migration) with ncclSend/ncclRecv. ---- */
 int sph_comm_unique_id(uint8_t out[128]);
+int sph_slab_plan(int32_t rz, int32_t world, int32_t rank, int32_t *z0, int32_t *z1); /* owned layers [z0, z1) */
+int sph_slab_create(const sph_config *cfg, sph_context **out);
+/* out8 = rank, world, z0, z1, first local layer, local layers, owned particles, mean particles sent per step */
+int sph_slab_info(const sph_context *ctx, int32_t out8[8]);
+/* Owned particles in canonical order (not indexed by id; ids are in the records).  Works without slab mode too. */
+int sph_download_owned(sph_context *ctx, sph_particle *aos, uint32_t capacity, uint32_t *n_out);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,8 @@ gmu_sim *gmu_sim_create(const char *type, float box_x, float box_y, float box_z,
 void gmu_sim_destroy(gmu_sim *s);
 const char *gmu_sim_last_error(void);
 
+/* multi-GPU extension: make the simulator rank `rank` of `world` z-slabs; call before gmu_sim_setup_scene */
+int gmu_sim_enable_slab(gmu_sim *s, int rank, int world, const unsigned char *nccl_id128);
 int gmu_sim_setup_scene(gmu_sim *s);                               /* setupScene() */
 int gmu_sim_step(gmu_sim *s, int n);                               /* n timer ticks: doWork() = step() + counters */
 int gmu_sim_step_many(gmu_sim *s, int n, double *device_ms);       /* fused device steps (extension) */
