@@ -149,6 +149,7 @@ def host_lib():
             "gmu_sim_destroy": (None, [vp]),
             "gmu_sim_last_error": (C.c_char_p, []),
             "gmu_sim_enable_slab": (i32, [vp, i32, i32, vp]),
+            "gmu_sim_set_owned_layers": (i32, [vp, i32, i32]),
             "gmu_sim_setup_scene": (i32, [vp]),
             "gmu_sim_step": (i32, [vp, i32]),
             "gmu_sim_step_many": (i32, [vp, i32, C.POINTER(dbl)]),
@@ -448,6 +449,10 @@ class Simulator:
     def _ck(self, rc):
         if rc:
             raise SphError(self.lib.gmu_sim_last_error().decode())
+
+    def set_owned_layers(self, z0, z1):
+        self._ck(self.lib.gmu_sim_set_owned_layers(self._h, int(z0), int(z1)))
+        return self
 
     def enable_slab(self, rank, world, nccl_id):
         buf = (C.c_uint8 * 128).from_buffer_copy(bytes(nccl_id)[:128].ljust(128, b"\0"))

@@ -32,7 +32,7 @@ void CBaseParticleSimulator::setupScene() {
     const unsigned int calculatedCount =
         (unsigned)(std::ceil(m_boxSize.z() / halfParticle) * std::ceil(m_boxSize.y() / halfParticle) *
                    std::ceil(m_boxSize.x() / 4 / halfParticle));
-    if (reserveWholeScene()) m_clParticles.reserve(calculatedCount);
+    if (!filtersScene()) m_clParticles.reserve(calculatedCount);
 
     if (m_scenario == DAM_BREAK) {
         const QVector3D offset = -m_boxSize / 2.0f;
@@ -48,10 +48,19 @@ void CBaseParticleSimulator::setupScene() {
     }
 }
 
+bool CBaseParticleSimulator::ownsParticle(float z) const {
+    if (!filtersScene()) return true;
+    // the z-layer exactly as updateGrid computes it (src/CCPUParticleSimulator.cpp:48,64-70)
+    int layer = (int)std::floor(((double)z + (double)m_boxSize.z() / 2.0) / (double)CParticle::h);
+    if (layer < 0) layer = 0;
+    else if (layer >= m_grid->zRes()) layer = m_grid->zRes() - 1;
+    return layer >= m_ownedZ0 && layer < m_ownedZ1;
+}
+
 void CBaseParticleSimulator::addParticle(float x, float y, float z, cl_float3 initialVelocity) {
     // :67-74 without the per-particle Qt3D entity; the id is the global running count
     const cl_uint id = m_nextParticleId++;
-    if (!ownsParticle(x, y, z)) return;
+    if (!ownsParticle(z)) return;
     m_clParticles.emplace_back(x, y, z, id, initialVelocity);
     m_particlesCount++;
 }

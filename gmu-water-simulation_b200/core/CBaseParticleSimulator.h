@@ -77,6 +77,8 @@ public:
     const std::vector<CParticle::Physics> &getHostParticles() const { return m_clParticles; }
     // fountain: number of 7-particle nozzles fired per step (1 = the reference's behaviour)
     void setEmissionMultiplier(int nozzles) { m_emissionMultiplier = nozzles < 1 ? 1 : nozzles; }
+    // slab decomposition: keep only the particles of z-layers [z0, z1) when the scene is generated
+    void setOwnedLayers(int z0, int z1) { m_ownedZ0 = z0; m_ownedZ1 = z1; }
 
 protected:
     struct alignas(16) SystemParams {
@@ -103,11 +105,12 @@ protected:
     virtual double updateCollisions() = 0;
     virtual double integrate() = 0;
 
-    // Extension for the slab-decomposed simulator: scene generation walks the WHOLE scene (ids are the global
-    // running count, as in the reference) but only keeps the particles this instance owns.
-    virtual bool ownsParticle(float /*x*/, float /*y*/, float /*z*/) { return true; }
-    virtual bool reserveWholeScene() { return true; }
-    cl_uint m_nextParticleId = 0;  // global running count (== m_particlesCount unless the scene is filtered)
+    // Extension for slab decomposition: scene generation walks the WHOLE scene (ids are the global running
+    // count, as in the reference) but only keeps the particles whose z-layer lies in [m_ownedZ0, m_ownedZ1).
+    bool ownsParticle(float z) const;
+    bool filtersScene() const { return m_ownedZ1 >= 0; }
+    int m_ownedZ0 = 0, m_ownedZ1 = -1;  // -1: no filter (own everything)
+    cl_uint m_nextParticleId = 0;       // global running count (== m_particlesCount unless the scene is filtered)
 
     bool isRunning() { return m_timer.isActive(); }
     void emitIterationChanged(unsigned long it) { for (auto &cb : m_iterationChanged) cb(it); }

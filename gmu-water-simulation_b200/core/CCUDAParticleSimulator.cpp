@@ -29,15 +29,7 @@ void CCUDAParticleSimulator::enableSlab(int rank, int world, const unsigned char
     m_world = world;
     std::memcpy(m_ncclId, ncclId, 128);
     if (sph_slab_plan(m_grid->zRes(), world, rank, &m_z0, &m_z1) != SPH_OK) throw CUDAException(sph_last_error(nullptr));
-}
-
-bool CCUDAParticleSimulator::ownsParticle(float, float, float z) {
-    if (!m_slab) return true;
-    // the z-layer exactly as updateGrid computes it (src/CCPUParticleSimulator.cpp:48,64-70)
-    int layer = (int)std::floor(((double)z + (double)m_boxSize.z() / 2.0) / (double)CParticle::h);
-    if (layer < 0) layer = 0;
-    else if (layer >= m_grid->zRes()) layer = m_grid->zRes() - 1;
-    return layer >= m_z0 && layer < m_z1;
+    setOwnedLayers(m_z0, m_z1);
 }
 
 void CCUDAParticleSimulator::setupScene() {

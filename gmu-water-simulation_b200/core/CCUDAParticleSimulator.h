@@ -52,9 +52,6 @@ protected:
     double updateCollisions() override;
     double integrate() override;
 
-    bool ownsParticle(float x, float y, float z) override;
-    bool reserveWholeScene() override { return !m_slab; }
-
 private:
     void pushNewParticles();
 

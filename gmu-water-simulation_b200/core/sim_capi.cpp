@@ -104,6 +104,10 @@ int gmu_sim_emit(gmu_sim *s, int n_steps) {
     return guarded([&] { for (int k = 0; k < n_steps; ++k) H(s)->sim->doWork(); });
 }
 
+int gmu_sim_set_owned_layers(gmu_sim *s, int z0, int z1) {
+    return guarded([&] { H(s)->sim->setOwnedLayers(z0, z1); });
+}
+
 int gmu_sim_enable_slab(gmu_sim *s, int rank, int world, const unsigned char *nccl_id128) {
     return guarded([&] {
         if (!H(s)->cuda) throw std::runtime_error("gmu_sim_enable_slab: not a CUDA simulator");

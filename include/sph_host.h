@@ -24,6 +24,8 @@ void gmu_sim_destroy(gmu_sim *s);
 const char *gmu_sim_last_error(void);
 
 /* multi-GPU extension: make the simulator rank `rank` of `world` z-slabs; call before gmu_sim_setup_scene */
+/* host half of the slab split: keep only the particles of z-layers [z0, z1) at scene generation (any simulator type) */
+int gmu_sim_set_owned_layers(gmu_sim *s, int z0, int z1);
 int gmu_sim_enable_slab(gmu_sim *s, int rank, int world, const unsigned char *nccl_id128);
 int gmu_sim_setup_scene(gmu_sim *s);                               /* setupScene() */
 int gmu_sim_step(gmu_sim *s, int n);                               /* n timer ticks: doWork() = step() + counters */

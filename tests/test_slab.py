@@ -1,0 +1,123 @@
+"""Slab decomposition (multi-GPU extension): host logic on CPU (incl. a world_size-2 gloo run) and the
+device path on however many GPUs the box has."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle_binding import Oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("rz,world", [(33, 2), (3200, 8), (800, 2), (17, 4), (101, 3)])
+def test_slab_plan_is_a_partition(gws, rz, world):
+    edges = [gws.slab_plan(rz, world, r) for r in range(world)]
+    assert edges[0][0] == 0 and edges[-1][1] == rz
+    for (a0, a1), (b0, b1) in zip(edges, edges[1:]):
+        assert a1 == b0 and a1 - a0 >= 4
+    sizes = [b - a for a, b in edges]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_slab_plan_rejects_thin_slabs(gws):
+    with pytest.raises(gws.SphError):
+        gws.slab_plan(15, 4, 0)
+    with pytest.raises(gws.SphError):
+        gws.slab_plan(100, 4, 4)
+
+
+def test_scene_partition_matches_oracle(gws):
+    """Each rank keeps exactly the particles whose z-layer (the oracle's key formula) it owns; ids stay global."""
+    box = (0.5, 0.3, 1.2)
+    o = Oracle(box).setup_scene()
+    rz = o.grid_res[2]
+    layer = o.keys() // (o.grid_res[0] * o.grid_res[1])  # all particles are still in their lattice positions
+    seen = np.zeros(o.n, dtype=np.int32)
+    for rank in range(3):
+        z0, z1 = gws.slab_plan(rz, 3, rank)
+        sim = gws.Simulator("scene_only", box).set_owned_layers(z0, z1).setup_scene()
+        hp = sim.host_particles()
+        ids = hp["id"].astype(np.int64)
+        assert np.array_equal(ids, np.flatnonzero((layer >= z0) & (layer < z1)))
+        assert np.array_equal(hp["position"][:, :3].view(np.uint32), o.pos[ids].view(np.uint32))
+        assert sim.max_count == o.n  # the scene size stays the global one
+        seen[ids] += 1
+    assert np.all(seen == 1)
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+import torch, torch.distributed as dist
+import gmu_water_simulation_b200 as gws
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+box = (0.4, 0.4, 0.9)
+ident = [bytes(range(128)) if rank == 0 else None]       # stands in for the NCCL id: same plumbing as bench.py
+dist.broadcast_object_list(ident, src=0)
+assert ident[0] == bytes(range(128))
+rz = int(gws.make_config(box, 1).grid_res[2])
+z0, z1 = gws.slab_plan(rz, world, rank)
+sim = gws.Simulator("scene_only", box).set_owned_layers(z0, z1).setup_scene()
+ids = sim.host_particles()["id"].astype(np.int64)
+t = torch.tensor([sim.n, int(ids.sum()), int(ids.min()), int(ids.max())], dtype=torch.int64)
+parts = [torch.zeros_like(t) for _ in range(world)]
+dist.all_gather(parts, t)
+total = sum(int(p[0]) for p in parts)
+n_all = sim.max_count
+assert total == n_all, (total, n_all)
+assert sum(int(p[1]) for p in parts) == n_all * (n_all - 1) // 2      # every id exactly once
+agg = torch.tensor([float(sim.n)], dtype=torch.float64)
+dist.all_reduce(agg, op=dist.ReduceOp.SUM)                             # the bench's whole-job aggregation
+assert int(agg.item()) == n_all
+if rank == 0:
+    print("GLOO SLAB OK", total)
+dist.destroy_process_group()
+'''
+
+
+def test_world2_gloo_scene_partition(tmp_path):
+    """N>1 host path on CPU: rendezvous + id broadcast + slab plan + per-rank scene generation + aggregation."""
+    worker = tmp_path / "worker.py"
+    worker.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(worker), ROOT]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "GLOO SLAB OK" in out.stdout
+
+
+@pytest.mark.gpu
+def test_single_rank_slab_equals_plain_run(gws):
+    """world == 1 slab mode (no neighbours) runs the slab step loop; results must equal the plain path bitwise."""
+    box = (0.4, 0.4, 0.9)
+    plain = gws.Simulator("cuda", box).setup_scene()
+    slab = gws.Simulator("cuda", box).enable_slab(0, 1, bytes(128)).setup_scene()
+    plain.step_many(12)
+    slab.step_many(12)
+    plain.sync_host()
+    a = plain.host_particles()
+    b = slab.context().download_owned()
+    order = np.argsort(b["id"], kind="stable")
+    b = b[order]
+    assert np.array_equal(b["id"], a["id"])
+    for f in ("position", "velocity", "density", "cell_id"):
+        assert np.array_equal(a[f].view(np.uint32), b[f].view(np.uint32)), f
+    info = slab.context().slab_info()
+    assert info["n_own"] == plain.n and info["z0"] == 0
+
+
+@pytest.mark.gpu
+def test_two_rank_slab_equivalence(gws):
+    """2 ranks on 2 GPUs vs one GPU (tools/slab_check.py); skipped on single-GPU boxes."""
+    if gws.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(ROOT, "tools", "slab_check.py"), "--steps", "20"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "SLAB CHECK OK" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])
