@@ -38,6 +38,7 @@ WORKLOADS = {
     "dam_break_250K": ((2.28, 2.28, 2.28), 250000),
     "dam_break_32K": ((1.14, 1.14, 1.14), 32500),
     "dam_break_16K": ((0.9, 0.9, 0.9), 16000),
+    "tank_8M": ((4.56, 4.56, 146.23 / 8.0), 8000000),  # one GPU's share of the 64M tank, without slabs
 }
 # N > 1: the elongated tank of BASELINE configs[4], z-slabs of 400 cell layers (8,000,000 particles) per GPU;
 # at N = 8 this is exactly the 64,000,000-particle tank 4.56 x 4.56 x 146.23
