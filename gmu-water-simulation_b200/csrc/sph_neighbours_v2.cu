@@ -71,7 +71,7 @@ __device__ __forceinline__ void ld256(const float4 *p, float4 &a, float4 &b) {
 // ================================================================= density + pressure + hit bitmask
 // Word format: bit 31 = first candidate of the word (index j0), bit 31-k = candidate j0+k.
 // Stored as uint2 {bits, j0 + 31} so that the force pass gets j = (j0 + 31) - msb_index(bits).
-__global__ void __launch_bounds__(128) k_density_mask(const float *__restrict__ xs, const float *__restrict__ ys,
+__global__ void __launch_bounds__(128, 8) k_density_mask(const float *__restrict__ xs, const float *__restrict__ ys,
                                                       const float *__restrict__ zs, const float4 *__restrict__ vel,
                                                       const int *__restrict__ key, const int *__restrict__ cell_start,
                                                       float4 *__restrict__ dp, float4 *__restrict__ fdat,
