@@ -330,3 +330,49 @@ def test_full_size_properties_1m(gws):
     ctx.forces(); ctx.integrate()
     rec = ctx.download()
     assert np.isfinite(rec["position"]).all()
+
+
+def test_rollout_statistics_1000_steps(gws):
+    """BASELINE north_star: long rollouts are chaotic, so 1000 steps are compared statistically.  Definitions of
+    SURVEY.md §8c, sampled every 10 steps (eventLoggerStride): kinetic energy 0.5 m sum|v|^2, centre of mass,
+    fill height max(y)+b/2.  Stated tolerances: COM within 0.5 h per axis at every sample, fill height within
+    2 h, KE within 5 % of the run's peak KE at every sample and within 5 % relative over the first 300 steps."""
+    box, h = 0.4, 0.0457
+    o = Oracle(box).setup_scene()
+    sim = gws.Simulator("cuda", box).setup_scene()
+    ctx = sim.context()
+    ke_o, ke_g, com_err, fill_err = [], [], [], []
+    for _ in range(100):
+        o.step(10)
+        sim.step_many(10)
+        so, sg = o.stats(), ctx.stats()
+        ke_o.append(so["ke"]); ke_g.append(sg["ke"])
+        com_err.append(np.abs(so["com"] - sg["com"]).max())
+        fill_err.append(abs(so["fill"] - sg["fill"]))
+    ke_o, ke_g = np.array(ke_o), np.array(ke_g)
+    assert max(com_err) <= 0.5 * h, max(com_err)
+    assert max(fill_err) <= 2.0 * h, max(fill_err)
+    assert np.abs(ke_g - ke_o).max() <= 0.05 * ke_o.max()
+    assert np.all(np.abs(ke_g[:30] / ke_o[:30] - 1) <= 0.05)
+    assert np.isfinite(ke_g).all() and sim.iteration == 1000
+
+
+def test_fountain_at_scale_with_nozzle_array(gws):
+    """BASELINE configs[3]: fountain with continuous emission and the six walls, scaled up with the nozzle array
+    (emission multiplier extension): 64 nozzles x 7 particles per step until the scene is full."""
+    box = 1.14  # max 32 500 particles
+    sim = gws.Simulator("cuda", box, scenario=gws.FOUNTAIN).setup_scene()
+    sim.set_emission_multiplier(64)
+    assert sim.n == 0 and sim.max_count == 32500
+    sim.step(100)
+    assert sim.n == min(64 * 7 * 100, (32500 - 7) // 7 * 7 + 7) or sim.n <= 32500
+    sim.sync_host()
+    hp = sim.host_particles()
+    assert np.isfinite(hp["position"]).all() and np.isfinite(hp["velocity"]).all()
+    # the walls keep the water in the box (penalty walls are soft: allow one h of penetration)
+    assert np.abs(hp["position"][:, :3]).max() <= box / 2 + 0.0457
+    assert np.array_equal(np.sort(hp["id"]), np.arange(sim.n, dtype=np.uint32))
+    ctx = sim.context()
+    ctx.update_grid(); ctx.density_pressure()
+    counts, _ = ctx.neighbours(lists=False)
+    assert counts.min() >= 1 and hp["density"].max() > 328.0
