@@ -40,9 +40,10 @@ WORKLOADS = {
     "dam_break_16K": ((0.9, 0.9, 0.9), 16000),
     "tank_8M": ((4.56, 4.56, 146.23 / 8.0), 8000000),  # one GPU's share of the 64M tank, without slabs
 }
-# N > 1: the elongated tank of BASELINE configs[4], z-slabs of 400 cell layers (8,000,000 particles) per GPU;
-# at N = 8 this is exactly the 64,000,000-particle tank 4.56 x 4.56 x 146.23
-TANK_XY, TANK_Z_PER_GPU, TANK_PARTICLES_PER_GPU = 4.56, 146.23 / 8.0, 8000000
+# N > 1: BASELINE configs[4] — the elongated dam-break tank 4.56 x 4.56 x 146.23 with exactly 64,000,000
+# particles (100 x 100 x 3200 cells), slab-decomposed along z over the N GPUs: the total work is fixed ("strong").
+TANK_BOX = (4.56, 4.56, 146.23)
+WORKLOADS["tank_64M"] = (TANK_BOX, 64000000)
 
 
 def measured_peaks():
@@ -189,8 +190,8 @@ def run_ours(args):
 
     slab = world > 1
     if slab:
-        workload = f"tank_{8 * world}M_slabs"
-        box = (TANK_XY, TANK_XY, TANK_Z_PER_GPU * world)
+        workload = "tank_64M"
+        box = TANK_BOX
         ident = [gws.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ident, src=0)
         sim = gws.Simulator("cuda", box, device=local).enable_slab(rank, world, ident[0]).setup_scene()
@@ -260,12 +261,18 @@ def run_ours(args):
 
     peak, peak_src = measured_peaks()
     top = max(("density", "forces"), key=lambda k: phase_ms[k])
+    kernel_name = {"density": "k_density_mask", "forces": "k_forces_mask"}[top]
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    if os.path.exists(tpath) and workload == "dam_break_1M":
+        with open(tpath) as f:
+            traffic = json.load(f).get(kernel_name)
     top_bytes = KERNEL_ALG_BYTES[top] * n
     top_gbs = top_bytes / (phase_ms[top] * 1e-3) / 1e9
     step_gbs = value / world * ALG_BYTES_PER_PARTICLE_STEP / 1e9
     roofline = {
-        "bound": "hbm", "kernel": f"k_{top}", "achieved": top_gbs, "peak": peak, "unit": "GB/s", "frac": top_gbs / peak,
-        "traffic": None, "peak_source": peak_src,
+        "bound": "hbm", "kernel": kernel_name, "achieved": top_gbs, "peak": peak, "unit": "GB/s", "frac": top_gbs / peak,
+        "traffic": traffic, "peak_source": peak_src,
         "alg_bytes_per_launch": top_bytes,
         "kernel_ms": phase_ms[top],
         "step_level": {"alg_bytes_per_particle_step": ALG_BYTES_PER_PARTICLE_STEP, "achieved": step_gbs, "frac": step_gbs / peak},
@@ -287,18 +294,35 @@ def run_ours(args):
                "d2h_bytes_per_step": 80 * n * world, "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_sec / args.e2e_steps,
                "path": "CCUDAParticleSimulator::step(), MirrorMode::RoundTrip (pinned 80-byte AoS host mirror up and down every step)"}
 
+    device_name = sim.device
+    grid_res = list(ctx.grid_res)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sim.sync_host()
         hp = sim.host_particles()
         cpu = cpu_baseline_sample(hp["position"][:, :3].copy(), hp["velocity"][:, :3].copy(), box, args.cpu_seconds)
 
+    scaling_baseline = None
+    if args.scaling_baseline and workload != "tank_64M":
+        # the N>1 runs decompose the fixed 64M tank; this is the same tank on this one GPU (no slabs)
+        del sim, ctx
+        big = gws.Simulator("cuda", TANK_BOX, device=local).setup_scene()
+        big.step_many(1, timed=False)
+        big.step_many(max(args.preroll - 1, 1), timed=False)
+        big.step_many(3)
+        big_steps = min(args.steps, 30)
+        big_ms = big.step_many(big_steps)
+        scaling_baseline = {"workload": "tank_64M", "particles": big.n, "value": big.n * big_steps / (big_ms * 1e-3),
+                            "unit": UNIT, "ms_per_step": big_ms / big_steps, "steps": big_steps,
+                            "note": "denominator for the strong-scaling series run with --gpus 2/4/8"}
+        device_name = big.device
+        del big
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "particles_per_gpu": n, "box": list(box), "grid": list(ctx.grid_res),
+            "config": {"workload": workload, "particles_per_gpu": n, "box": list(box), "grid": grid_res,
                        "preroll_steps": args.preroll, "mean_neighbours": mean_nb,
                        "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (slab mode pending)",
                        "l2": "L2 evicted (256 MiB scratch write) before every timed step" if args.flush_l2 else "no eviction"},
@@ -310,7 +334,8 @@ def run_ours(args):
             "phase_ms": phase_ms,
             "value_warm_l2": total_particles * args.steps / (warm_ms * 1e-3),
             "wall_ms_per_step": 1e3 * wall / args.steps,
-            "device": sim.device,
+            "device": device_name,
+            "scaling_baseline": scaling_baseline,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -336,13 +361,13 @@ def finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, 
         step_gbs = value / world * ALG_BYTES_PER_PARTICLE_STEP / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "particles": int(total_particles), "box": list(box),
                        "preroll_steps": args.preroll,
                        "parallelism": f"{world} z-slabs, ghost+migration exchange per step via ncclSend/ncclRecv",
                        "slabs": [{k: i[k] for k in ("z0", "z1", "n_own", "mean_sent_per_step")} for i in infos],
-                       "l2": "no eviction: per-GPU working set (~2.5 GB) is far larger than the 126 MB L2"},
+                       "l2": "no eviction: the per-GPU working set (GBs) is far larger than the 126 MB L2"},
             "clocks": clocks.summary(),
             "e2e": {"value": total_particles * args.e2e_steps / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": int(80 * total_particles), "steps": args.e2e_steps,
@@ -371,6 +396,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scaling-baseline", dest="scaling_baseline", action="store_false",
+                    help="skip the single-GPU run of the 64M tank (denominator of the strong-scaling series)")
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")
     ap.add_argument("--neighbour-variant", type=int, default=None)
     args = ap.parse_args()
