@@ -78,6 +78,12 @@ struct Slab {
     int *d_counters = nullptr;  // [0] to lower, [1] to upper, [2] from lower, [3] from upper
     ncclComm_t comm = nullptr;
     uint64_t sent_particles = 0, exchanges = 0;
+    // overlapped exchange: pack + NCCL run on their own stream while the interior of the slab is still computing
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_ranges = nullptr, ev_boundary = nullptr, ev_counts = nullptr, ev_comm = nullptr;
+    bool have_ghosts = false;  // A already holds this step's ghosts/migrants behind the owned particles
+    int *h_pinned = nullptr;   // 8 ints of pinned host memory for the small read-backs
+    int opt_overlap = 1;
 };
 
 namespace {
@@ -196,13 +202,13 @@ void enqueue_density(sph_context *c) {
 }
 void enqueue_forces(sph_context *c) {
     if (use_mask_passes(c))
-        launch_forces_mask(c->nb, c->dp, c->nb_count, c->g.key_s, c->g.cell_start, c->acc, (int)c->n, c->P, c->stream);
+        launch_forces_mask(c->nb, c->dp, c->nb_count, c->g.key_s, c->g.cell_start, c->acc, 0, (int)c->n, c->P, c->stream);
     else
         launch_forces(c->pos_s, c->vel_s, c->dp, c->g.key_s, c->g.cell_start, c->acc, (int)c->n, c->P, 0, c->stream);
     c->kernel_launches += 1;
 }
 void enqueue_integrate(sph_context *c) {
-    launch_integrate_collide(c->pos_s, c->vel_s, c->acc, c->pos_a, c->vel_a, (int)c->n, c->P, c->stream);
+    launch_integrate_collide(c->pos_s, c->vel_s, c->acc, c->pos_a, c->vel_a, 0, (int)c->n, nullptr, nullptr, c->P, c->stream);
     c->kernel_launches += 1;
     c->in_off = 0;  // integrate writes A[0, n) in canonical order
 }
@@ -284,6 +290,10 @@ void slab_release(sph_context *c) {
     }
     for (void *p : {(void *)s->down_pos, (void *)s->down_vel, (void *)s->up_pos, (void *)s->up_vel, (void *)s->d_counters})
         if (p) cudaFree(p);
+    if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    for (cudaEvent_t e : {s->ev_ranges, s->ev_boundary, s->ev_counts, s->ev_comm})
+        if (e) cudaEventDestroy(e);
+    if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
     delete s;
     c->slab = nullptr;
 }
@@ -298,85 +308,194 @@ void slab_plan(int rz, int world, int rank, int *z0, int *z1) {
 // Ghost exchange + migration in one message pair per face.  Every rank sends, to each neighbour, its
 // particles lying in the two layers on either side of the shared face (ghosts for the neighbour) or beyond
 // it (migrants); the receiver appends them behind its own particles and the ordinary grid build sorts all.
-int slab_exchange(sph_context *c) {
+//
+// The exchange is split in three stream-ordered pieces so that the overlapped step can run them on the
+// communication stream: pack (one or two index ranges of A), counts (4-byte messages, then read back),
+// payload (exact sizes, received straight into the tail of A).
+void slab_pack_begin(sph_context *c, cudaStream_t st) { cudaMemsetAsync(c->slab->d_counters, 0, 4 * sizeof(int), st); }
+
+void slab_pack_range(sph_context *c, cudaStream_t st, uint32_t first, uint32_t count) {
+    Slab &s = *c->slab;
+    const bool has_down = s.rank > 0, has_up = s.rank + 1 < s.world;
+    launch_slab_pack(c->pos_a + first, c->vel_a + first, (int)count, has_down ? s.z0 + 2 : -1, has_up ? s.z1 - 2 : 0x7fffffff,
+                     s.down_pos, s.down_vel, s.up_pos, s.up_vel, s.d_counters, s.cap_face, c->P, st);
+    c->kernel_launches += 1;
+}
+
+// counts[0..1] = particles this rank sends down/up, counts[2..3] = particles it will receive from below/above
+int slab_exchange_counts(sph_context *c, cudaStream_t st, int counts[4]) {
     Slab &s = *c->slab;
     NcclApi *api = nccl_api(&c->err);
     if (!api) return SPH_ERR_COMM;
     const bool has_down = s.rank > 0, has_up = s.rank + 1 < s.world;
-    float4 *pa = c->pos_a + c->in_off, *va = c->vel_a + c->in_off;
-    CUDA_TRY(c, cudaMemsetAsync(s.d_counters, 0, 4 * sizeof(int), c->stream));
-    launch_slab_pack(pa, va, (int)s.n_own, has_down ? s.z0 + 2 : -1, has_up ? s.z1 - 2 : 0x7fffffff, s.down_pos, s.down_vel,
-                     s.up_pos, s.up_vel, s.d_counters, s.cap_face, c->P, c->stream);
-    c->kernel_launches += 1;
-    // the counts travel first (4-byte messages), then the payloads with their exact sizes
     NCCL_TRY(c, api, api->GroupStart());
     if (has_down) {
-        NCCL_TRY(c, api, api->Send(s.d_counters + 0, 1, ncclInt32, s.rank - 1, s.comm, c->stream));
-        NCCL_TRY(c, api, api->Recv(s.d_counters + 2, 1, ncclInt32, s.rank - 1, s.comm, c->stream));
+        NCCL_TRY(c, api, api->Send(s.d_counters + 0, 1, ncclInt32, s.rank - 1, s.comm, st));
+        NCCL_TRY(c, api, api->Recv(s.d_counters + 2, 1, ncclInt32, s.rank - 1, s.comm, st));
     }
     if (has_up) {
-        NCCL_TRY(c, api, api->Send(s.d_counters + 1, 1, ncclInt32, s.rank + 1, s.comm, c->stream));
-        NCCL_TRY(c, api, api->Recv(s.d_counters + 3, 1, ncclInt32, s.rank + 1, s.comm, c->stream));
+        NCCL_TRY(c, api, api->Send(s.d_counters + 1, 1, ncclInt32, s.rank + 1, s.comm, st));
+        NCCL_TRY(c, api, api->Recv(s.d_counters + 3, 1, ncclInt32, s.rank + 1, s.comm, st));
     }
     NCCL_TRY(c, api, api->GroupEnd());
-    int h[4] = {0, 0, 0, 0};
-    CUDA_TRY(c, cudaMemcpyAsync(h, s.d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    const int send_down = h[0], send_up = h[1], recv_down = has_down ? h[2] : 0, recv_up = has_up ? h[3] : 0;
-    REQUIRE(c, send_down <= s.cap_face && send_up <= s.cap_face, SPH_ERR_STATE, "slab: face buffer overflow");
-    REQUIRE(c, (uint64_t)c->in_off + s.n_own + (uint64_t)recv_down + (uint64_t)recv_up <= c->cap, SPH_ERR_STATE,
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_pinned, s.d_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaEventRecord(s.ev_counts, st));
+    CUDA_TRY(c, cudaEventSynchronize(s.ev_counts));  // only this stream's work is waited for
+    counts[0] = s.h_pinned[0];
+    counts[1] = s.h_pinned[1];
+    counts[2] = has_down ? s.h_pinned[2] : 0;
+    counts[3] = has_up ? s.h_pinned[3] : 0;
+    REQUIRE(c, counts[0] <= s.cap_face && counts[1] <= s.cap_face, SPH_ERR_STATE, "slab: face buffer overflow");
+    return SPH_OK;
+}
+
+int slab_exchange_payload(sph_context *c, cudaStream_t st, const int counts[4], uint32_t dst_first) {
+    Slab &s = *c->slab;
+    NcclApi *api = nccl_api(&c->err);
+    if (!api) return SPH_ERR_COMM;
+    const bool has_down = s.rank > 0, has_up = s.rank + 1 < s.world;
+    REQUIRE(c, (uint64_t)dst_first + (uint64_t)counts[2] + (uint64_t)counts[3] <= c->cap, SPH_ERR_STATE,
             "slab: local particle capacity exceeded");
-    float4 *rp = pa + s.n_own, *rv = va + s.n_own;
+    float4 *rp = c->pos_a + dst_first, *rv = c->vel_a + dst_first;
     NCCL_TRY(c, api, api->GroupStart());
     if (has_down) {
-        if (send_down) {
-            NCCL_TRY(c, api, api->Send(s.down_pos, (size_t)send_down * 4, ncclFloat32, s.rank - 1, s.comm, c->stream));
-            NCCL_TRY(c, api, api->Send(s.down_vel, (size_t)send_down * 4, ncclFloat32, s.rank - 1, s.comm, c->stream));
+        if (counts[0]) {
+            NCCL_TRY(c, api, api->Send(s.down_pos, (size_t)counts[0] * 4, ncclFloat32, s.rank - 1, s.comm, st));
+            NCCL_TRY(c, api, api->Send(s.down_vel, (size_t)counts[0] * 4, ncclFloat32, s.rank - 1, s.comm, st));
         }
-        if (recv_down) {
-            NCCL_TRY(c, api, api->Recv(rp, (size_t)recv_down * 4, ncclFloat32, s.rank - 1, s.comm, c->stream));
-            NCCL_TRY(c, api, api->Recv(rv, (size_t)recv_down * 4, ncclFloat32, s.rank - 1, s.comm, c->stream));
+        if (counts[2]) {
+            NCCL_TRY(c, api, api->Recv(rp, (size_t)counts[2] * 4, ncclFloat32, s.rank - 1, s.comm, st));
+            NCCL_TRY(c, api, api->Recv(rv, (size_t)counts[2] * 4, ncclFloat32, s.rank - 1, s.comm, st));
         }
     }
     if (has_up) {
-        if (send_up) {
-            NCCL_TRY(c, api, api->Send(s.up_pos, (size_t)send_up * 4, ncclFloat32, s.rank + 1, s.comm, c->stream));
-            NCCL_TRY(c, api, api->Send(s.up_vel, (size_t)send_up * 4, ncclFloat32, s.rank + 1, s.comm, c->stream));
+        if (counts[1]) {
+            NCCL_TRY(c, api, api->Send(s.up_pos, (size_t)counts[1] * 4, ncclFloat32, s.rank + 1, s.comm, st));
+            NCCL_TRY(c, api, api->Send(s.up_vel, (size_t)counts[1] * 4, ncclFloat32, s.rank + 1, s.comm, st));
         }
-        if (recv_up) {
-            NCCL_TRY(c, api, api->Recv(rp + recv_down, (size_t)recv_up * 4, ncclFloat32, s.rank + 1, s.comm, c->stream));
-            NCCL_TRY(c, api, api->Recv(rv + recv_down, (size_t)recv_up * 4, ncclFloat32, s.rank + 1, s.comm, c->stream));
+        if (counts[3]) {
+            NCCL_TRY(c, api, api->Recv(rp + counts[2], (size_t)counts[3] * 4, ncclFloat32, s.rank + 1, s.comm, st));
+            NCCL_TRY(c, api, api->Recv(rv + counts[2], (size_t)counts[3] * 4, ncclFloat32, s.rank + 1, s.comm, st));
         }
     }
     NCCL_TRY(c, api, api->GroupEnd());
-    c->n = s.n_own + (uint32_t)recv_down + (uint32_t)recv_up;
-    s.sent_particles += (uint64_t)send_down + (uint64_t)send_up;
+    s.sent_particles += (uint64_t)counts[0] + (uint64_t)counts[1];
     s.exchanges += 1;
     return SPH_OK;
 }
 
-int slab_step(sph_context *c, int n_steps, double *ms) {
+// Blocking exchange on the compute stream: pack the whole owned view, then counts, then payload.
+int slab_exchange(sph_context *c) {
+    Slab &s = *c->slab;
+    int counts[4];
+    slab_pack_begin(c, c->stream);
+    slab_pack_range(c, c->stream, c->in_off, s.n_own);
+    int rc = slab_exchange_counts(c, c->stream, counts);
+    if (rc) return rc;
+    rc = slab_exchange_payload(c, c->stream, counts, c->in_off + s.n_own);
+    if (rc) return rc;
+    c->n = s.n_own + (uint32_t)counts[2] + (uint32_t)counts[3];
+    s.have_ghosts = true;
+    return SPH_OK;
+}
+
+// Read back the first particle index of up to 4 local z-layers (cell_start at layer boundaries).
+int slab_layer_starts(sph_context *c, const int layers[4], int out[4]) {
+    Slab &s = *c->slab;
+    const size_t rxy = (size_t)c->P.rx * c->P.ry;
+    for (int k = 0; k < 4; ++k)
+        CUDA_TRY(c, cudaMemcpyAsync(s.h_pinned + 4 + k, c->g.cell_start + (size_t)layers[k] * rxy, sizeof(int),
+                                    cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaEventRecord(s.ev_ranges, c->stream));
+    return SPH_OK;
+}
+
+// Sequential slab step (exchange, then the ordinary step) — reference behaviour for the overlapped variant.
+int slab_step_sequential(sph_context *c, int n_steps, double *ms) {
     Slab &s = *c->slab;
     PhaseTimer t(c, ms);
     for (int k = 0; k < n_steps; ++k) {
-        int rc = slab_exchange(c);
-        if (rc) return rc;
+        if (!s.have_ghosts) {
+            int rc = slab_exchange(c);
+            if (rc) return rc;
+        }
         enqueue_step(c);
+        s.have_ghosts = false;
         // the owned particles are the contiguous run of the owned layers in the canonical order
-        const size_t rxy = (size_t)c->P.rx * c->P.ry;
-        int lo = 0, hi = 0;
-        CUDA_TRY(c, cudaMemcpyAsync(&lo, c->g.cell_start + (size_t)(s.z0 - s.z_base) * rxy, sizeof(int),
-                                    cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(c, cudaMemcpyAsync(&hi, c->g.cell_start + (size_t)(s.z1 - s.z_base) * rxy, sizeof(int),
-                                    cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        c->in_off = (uint32_t)lo;
-        s.n_own = (uint32_t)(hi - lo);
+        const int layers[4] = {s.z0 - s.z_base, s.z0 - s.z_base, s.z1 - s.z_base, s.z1 - s.z_base};
+        int rc = slab_layer_starts(c, layers, nullptr);
+        if (rc) return rc;
+        CUDA_TRY(c, cudaEventSynchronize(s.ev_ranges));
+        c->in_off = (uint32_t)s.h_pinned[4];
+        s.n_own = (uint32_t)(s.h_pinned[6] - s.h_pinned[4]);
     }
     c->steps += (uint64_t)n_steps;
     c->s_valid = c->grid_valid = c->density_valid = c->forces_valid = c->a_aligned = true;
     int rc = check_launch(c, "slab step");
     return rc ? rc : t.finish();
+}
+
+// Overlapped slab step.  After the density pass the forces + integration run first on the boundary layers
+// (the four owned layers next to each face: two that become the neighbour's ghosts plus two of slack for
+// particles moving towards the face), then on the interior.  As soon as the boundary is integrated the
+// communication stream packs it and runs the NCCL exchange for the NEXT step, concurrently with the interior
+// kernels; ghosts are neither force-evaluated nor integrated, so the received particles can land directly
+// behind the owned run of A while the interior is still being written.
+int slab_step_overlapped(sph_context *c, int n_steps, double *ms) {
+    Slab &s = *c->slab;
+    constexpr int kBoundaryLayers = 4;
+    PhaseTimer t(c, ms);
+    for (int k = 0; k < n_steps; ++k) {
+        if (!s.have_ghosts) {  // first step after an upload: nothing to overlap with yet
+            int rc = slab_exchange(c);
+            if (rc) return rc;
+        }
+        enqueue_grid(c);
+        const int l0 = s.z0 - s.z_base, l3 = s.z1 - s.z_base;
+        const int l1 = std::min(l0 + kBoundaryLayers, l3), l2 = std::max(l3 - kBoundaryLayers, l1);
+        const int layers[4] = {l0, l1, l2, l3};
+        int rc = slab_layer_starts(c, layers, nullptr);
+        if (rc) return rc;
+        enqueue_density(c);  // all local particles: the first ghost layer needs its density too
+        CUDA_TRY(c, cudaEventSynchronize(s.ev_ranges));  // returns while the density pass is still running
+        const int L0 = s.h_pinned[4], L1 = s.h_pinned[5], L2 = s.h_pinned[6], L3 = s.h_pinned[7];
+        auto forces_integrate = [&](int i0, int i1) {
+            launch_forces_mask(c->nb, c->dp, c->nb_count, c->g.key_s, c->g.cell_start, c->acc, i0, i1, c->P, c->stream);
+            launch_integrate_collide(c->pos_s, c->vel_s, c->acc, c->pos_a, c->vel_a, i0, i1, c->g.key_s, s.d_counters + 4,
+                                     c->P, c->stream);
+            c->kernel_launches += 2;
+        };
+        forces_integrate(L0, L1);
+        forces_integrate(L2, L3);
+        CUDA_TRY(c, cudaEventRecord(s.ev_boundary, c->stream));
+        forces_integrate(L1, L2);  // interior: overlaps with the exchange below
+        // ---- exchange for the next step on the communication stream
+        CUDA_TRY(c, cudaStreamWaitEvent(s.comm_stream, s.ev_boundary, 0));
+        slab_pack_begin(c, s.comm_stream);
+        slab_pack_range(c, s.comm_stream, (uint32_t)L0, (uint32_t)(L1 - L0));
+        slab_pack_range(c, s.comm_stream, (uint32_t)L2, (uint32_t)(L3 - L2));
+        int counts[4];
+        rc = slab_exchange_counts(c, s.comm_stream, counts);
+        if (rc) return rc;
+        rc = slab_exchange_payload(c, s.comm_stream, counts, (uint32_t)L3);
+        if (rc) return rc;
+        CUDA_TRY(c, cudaEventRecord(s.ev_comm, s.comm_stream));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, s.ev_comm, 0));  // the next grid build needs the received tail
+        c->in_off = (uint32_t)L0;
+        s.n_own = (uint32_t)(L3 - L0);
+        c->n = s.n_own + (uint32_t)counts[2] + (uint32_t)counts[3];
+        s.have_ghosts = true;
+    }
+    c->steps += (uint64_t)n_steps;
+    c->s_valid = c->grid_valid = c->density_valid = c->forces_valid = c->a_aligned = true;
+    int rc = check_launch(c, "slab step");
+    return rc ? rc : t.finish();
+}
+
+int slab_step(sph_context *c, int n_steps, double *ms) {
+    if (c->slab->opt_overlap && use_mask_passes(c) && (c->slab->z1 - c->slab->z0) >= 8)
+        return slab_step_overlapped(c, n_steps, ms);
+    return slab_step_sequential(c, n_steps, ms);
 }
 
 }  // namespace
@@ -554,7 +673,10 @@ int sph_upload_particles(sph_context *c, const sph_particle *aos, uint32_t n) {
     CUDA_TRY(c, cudaSetDevice(c->device));
     c->n = n;
     c->in_off = 0;
-    if (c->slab) c->slab->n_own = n;
+    if (c->slab) {
+        c->slab->n_own = n;
+        c->slab->have_ghosts = false;
+    }
     c->s_valid = c->grid_valid = c->a_aligned = c->density_valid = c->forces_valid = false;
     return upload_range(c, aos, 0, n);
 }
@@ -932,6 +1054,11 @@ int sph_set_option(sph_context *c, const char *name, int value) {
     else if (k == "use_graph") c->opt_use_graph = value;
     else if (k == "count_neighbours") c->opt_count_neighbours = value;
     else if (k == "flush_l2") { c->opt_flush_l2 = value; return SPH_OK; }
+    else if (k == "slab_overlap") {
+        REQUIRE(c, c->slab, SPH_ERR_STATE, "sph_set_option: slab_overlap needs a slab context");
+        c->slab->opt_overlap = value;
+        return SPH_OK;
+    }
     else return fail(c, SPH_ERR_ARGUMENT, "sph_set_option: unknown option " + k);
     drop_graph(c);
     return SPH_OK;
@@ -943,6 +1070,11 @@ int sph_get_counter(const sph_context *c, const char *name, uint64_t *value) {
     if (k == "kernel_launches") *value = c->kernel_launches;
     else if (k == "graph_launches") *value = c->graph_launches;
     else if (k == "steps") *value = c->steps;
+    else if (k == "slab_far_movers") {  // particles that crossed more than 2 z-layers in one step (must stay 0)
+        int v = 0;
+        if (c->slab) cudaMemcpy(&v, c->slab->d_counters + 4, sizeof(int), cudaMemcpyDeviceToHost);
+        *value = (uint64_t)v;
+    }
     else return SPH_ERR_ARGUMENT;
     return SPH_OK;
 }
@@ -1012,7 +1144,14 @@ int sph_slab_create(const sph_config *cfg, sph_context **out) {
     SLAB_TRY(dalloc(&s->down_vel, (size_t)s->cap_face));
     SLAB_TRY(dalloc(&s->up_pos, (size_t)s->cap_face));
     SLAB_TRY(dalloc(&s->up_vel, (size_t)s->cap_face));
-    SLAB_TRY(dalloc(&s->d_counters, (size_t)4));
+    SLAB_TRY(dalloc(&s->d_counters, (size_t)8));  // [0..3] exchange counts, [4] particles that moved > 2 layers
+    SLAB_TRY(cudaMemset(s->d_counters, 0, 8 * sizeof(int)));
+    SLAB_TRY(cudaMallocHost(reinterpret_cast<void **>(&s->h_pinned), 8 * sizeof(int)));
+    SLAB_TRY(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+    SLAB_TRY(cudaEventCreateWithFlags(&s->ev_ranges, cudaEventDisableTiming));
+    SLAB_TRY(cudaEventCreateWithFlags(&s->ev_boundary, cudaEventDisableTiming));
+    SLAB_TRY(cudaEventCreateWithFlags(&s->ev_counts, cudaEventDisableTiming));
+    SLAB_TRY(cudaEventCreateWithFlags(&s->ev_comm, cudaEventDisableTiming));
 #undef SLAB_TRY
     if (cfg->world > 1) {
         std::string why;

@@ -45,10 +45,12 @@ void launch_forces(const float4 *pos_s, const float4 *vel_s, const float4 *dp, c
                    float4 *acc, int n, const Params &P, int variant, cudaStream_t st);
 void launch_density_mask(const NbBuffers &nb, const float4 *vel_s, const int *key_s, const int *cell_start, float4 *dp,
                          int *nb_count, int n, const Params &P, cudaStream_t st);
+// [i0, i1) = index range of the canonical order to process (the whole array outside slab mode)
 void launch_forces_mask(const NbBuffers &nb, const float4 *dp, const int *nb_count, const int *key_s, const int *cell_start,
-                        float4 *acc, int n, const Params &P, cudaStream_t st);
+                        float4 *acc, int i0, int i1, const Params &P, cudaStream_t st);
+// far_movers (may be NULL): slab mode counter of particles that crossed more than 2 z-layers in this step
 void launch_integrate_collide(const float4 *pos_s, const float4 *vel_s, float4 *acc, float4 *pos_out, float4 *vel_out,
-                              int n, const Params &P, cudaStream_t st);
+                              int i0, int i1, const int *key_s, int *far_movers, const Params &P, cudaStream_t st);
 
 // all-pairs validation kernels (CGPUBruteParticleSimulator semantics)
 void launch_brute_density(const float4 *pos, float4 *dp, int *nb_count, int n, const Params &P, cudaStream_t st);

@@ -147,9 +147,10 @@ __device__ __forceinline__ float dot_exact(float ax, float ay, float az, float b
 
 __global__ void __launch_bounds__(256) k_integrate_collide(const float4 *__restrict__ pos, const float4 *__restrict__ vel,
                                                            float4 *__restrict__ acc, float4 *__restrict__ pos_out,
-                                                           float4 *__restrict__ vel_out, int n,
+                                                           float4 *__restrict__ vel_out, int i0, int n,
+                                                           const int *__restrict__ key, int *__restrict__ far_movers,
                                                            const __grid_constant__ Params P) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;  // particles [i0, n): slab mode runs sub-ranges
     if (i >= n) return;
     const float4 p = __ldg(pos + i);
     const float4 v = __ldg(vel + i);
@@ -187,15 +188,22 @@ __global__ void __launch_bounds__(256) k_integrate_collide(const float4 *__restr
     nv.y = __fdiv_rn(__fsub_rn(np.y, p.y), dt);
     nv.z = __fdiv_rn(__fsub_rn(np.z, p.z), dt);
     nv.w = 0.0f;
+    if (far_movers) {
+        // slab mode: the ghost exchange assumes a particle crosses at most 2 z-layers per step; count offenders
+        const int old_layer = __ldg(key + i) / (P.rx * P.ry) + P.z_base;
+        const int new_layer = cell_coord(np.z, P.hbz, P.h_d, P.rz_global);
+        if (abs(new_layer - old_layer) > 2) atomicAdd(far_movers, 1);
+    }
     pos_out[i] = np;  // written to the authoritative A buffers, in the canonical order of this step
     vel_out[i] = nv;
     acc[i] = a;  // total acceleration (SPH + walls), what updateForces leaves in the CPU path
 }
 
 void launch_integrate_collide(const float4 *pos_s, const float4 *vel_s, float4 *acc, float4 *pos_out, float4 *vel_out,
-                              int n, const Params &P, cudaStream_t st) {
-    if (n <= 0) return;
-    k_integrate_collide<<<(n + 255) / 256, 256, 0, st>>>(pos_s, vel_s, acc, pos_out, vel_out, n, P);
+                              int i0, int i1, const int *key_s, int *far_movers, const Params &P, cudaStream_t st) {
+    if (i1 <= i0) return;
+    k_integrate_collide<<<(i1 - i0 + 255) / 256, 256, 0, st>>>(pos_s, vel_s, acc, pos_out, vel_out, i0, i1, key_s,
+                                                               far_movers, P);
 }
 
 }  // namespace sph

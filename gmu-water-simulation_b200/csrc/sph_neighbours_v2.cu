@@ -210,9 +210,9 @@ __global__ void __launch_bounds__(128) k_forces_mask(const float *__restrict__ x
                                                      const float *__restrict__ zs, const float4 *__restrict__ fdat,
                                                      const float4 *__restrict__ dp, const uint2 *__restrict__ mask,
                                                      const int *__restrict__ nb_words, const int *__restrict__ key,
-                                                     const int *__restrict__ cell_start, float4 *__restrict__ acc, int n,
-                                                     const __grid_constant__ Params P) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                                                     const int *__restrict__ cell_start, float4 *__restrict__ acc,
+                                                     int i0, int n, const __grid_constant__ Params P) {
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;  // particles [i0, n): slab mode runs sub-ranges
     if (i >= n) return;
     float4 pi, vi;
     ld256(fdat + 2 * (size_t)i, pi, vi);
@@ -252,11 +252,11 @@ __global__ void __launch_bounds__(128) k_forces_mask(const float *__restrict__ x
 }
 
 void launch_forces_mask(const NbBuffers &nb, const float4 *dp, const int *nb_count, const int *key_s, const int *cell_start,
-                        float4 *acc, int n, const Params &P, cudaStream_t st) {
-    if (n <= 0) return;
+                        float4 *acc, int i0, int i1, const Params &P, cudaStream_t st) {
+    if (i1 <= i0) return;
     (void)nb_count;
-    k_forces_mask<<<(n + 127) / 128, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, nb.fdat, dp, nb.mask, nb.words, key_s, cell_start,
-                                                   acc, n, P);
+    k_forces_mask<<<(i1 - i0 + 127) / 128, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, nb.fdat, dp, nb.mask, nb.words, key_s,
+                                                         cell_start, acc, i0, i1, P);
 }
 
 }  // namespace sph
