@@ -110,6 +110,14 @@ def test_single_rank_slab_equals_plain_run(gws):
         assert np.array_equal(a[f].view(np.uint32), b[f].view(np.uint32)), f
     info = slab.context().slab_info()
     assert info["n_own"] == plain.n and info["z0"] == 0
+    assert slab.context().counter("slab_far_movers") == 0
+    # the sequential (non-overlapped) slab step gives the same bits
+    seq = gws.Simulator("cuda", box).enable_slab(0, 1, bytes(128)).setup_scene()
+    seq.context().set_option("slab_overlap", 0)
+    seq.step_many(12)
+    c = seq.context().download_owned()
+    c = c[np.argsort(c["id"], kind="stable")]
+    assert np.array_equal(b["position"].view(np.uint32), c["position"].view(np.uint32))
 
 
 @pytest.mark.gpu
@@ -117,7 +125,8 @@ def test_two_rank_slab_equivalence(gws):
     """2 ranks on 2 GPUs vs one GPU (tools/slab_check.py); skipped on single-GPU boxes."""
     if gws.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29534", os.path.join(ROOT, "tools", "slab_check.py"), "--steps", "20"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0 and "SLAB CHECK OK" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])
+    for extra in ([], ["--no-overlap"]):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", "29534", os.path.join(ROOT, "tools", "slab_check.py"), "--steps", "20"] + extra
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and "SLAB CHECK OK" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])

@@ -24,6 +24,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--box", type=float, nargs=3, default=[0.5, 0.5, 1.5])
     ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--no-overlap", action="store_true", help="sequential exchange-then-step instead of the overlapped step")
     a = ap.parse_args()
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     def log(msg):
@@ -39,6 +40,8 @@ def main():
 
     sim = gws.Simulator("cuda", tuple(a.box), device=local).enable_slab(rank, world, ident[0]).setup_scene()
     ctx = sim.context()
+    if a.no_overlap:
+        ctx.set_option("slab_overlap", 0)
     info0 = ctx.slab_info()
     log(f"slab ready {info0}")
     checks = {}
@@ -82,6 +85,8 @@ def main():
                 com = np.abs(merged["position"][:, :3].mean(axis=0) - hp["position"][:, :3].mean(axis=0)).max()
                 checks["com_abs_diff"] = float(com)
                 assert np.percentile(d, 95) <= 0.1 * 0.0457 and err <= 0.0457 and com <= 1e-4, checks
+    far = ctx.counter("slab_far_movers")
+    assert far == 0, f"{far} particles crossed more than 2 z-layers in one step"
     infos = [None] * world if rank == 0 else None
     dist.gather_object(ctx.slab_info(), infos, dst=0)
     if rank == 0:
