@@ -202,7 +202,8 @@ void enqueue_density(sph_context *c) {
 }
 void enqueue_forces(sph_context *c) {
     if (use_mask_passes(c))
-        launch_forces_mask(c->nb, c->dp, c->nb_count, c->g.key_s, c->g.cell_start, c->acc, 0, (int)c->n, c->P, c->stream);
+        launch_forces_mask(c->nb, c->dp, c->nb_count, c->g.key_s, c->g.cell_start, c->acc, 0, (int)c->n, c->P, c->stream),
+            c->kernel_launches += 1;  // main kernel + the (normally idle) overflow kernel
     else
         launch_forces(c->pos_s, c->vel_s, c->dp, c->g.key_s, c->g.cell_start, c->acc, (int)c->n, c->P, 0, c->stream);
     c->kernel_launches += 1;
@@ -463,7 +464,7 @@ int slab_step_overlapped(sph_context *c, int n_steps, double *ms) {
             launch_forces_mask(c->nb, c->dp, c->nb_count, c->g.key_s, c->g.cell_start, c->acc, i0, i1, c->P, c->stream);
             launch_integrate_collide(c->pos_s, c->vel_s, c->acc, c->pos_a, c->vel_a, i0, i1, c->g.key_s, s.d_counters + 4,
                                      c->P, c->stream);
-            c->kernel_launches += 2;
+            c->kernel_launches += 3;
         };
         forces_integrate(L0, L1);
         forces_integrate(L2, L3);
@@ -836,7 +837,7 @@ int sph_step(sph_context *c, int n_steps, double *ms) {
             if (c->graph_exec) {
                 CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, c->stream));
                 c->graph_launches += 1;
-                c->kernel_launches += kKernelsPerStep;
+                c->kernel_launches += kKernelsPerStep + (use_mask_passes(c) ? 1 : 0);
             } else {
                 enqueue_step(c);
             }
@@ -862,7 +863,7 @@ int sph_step(sph_context *c, int n_steps, double *ms) {
         if (c->graph_exec) {
             CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, c->stream));
             c->graph_launches += 1;
-            c->kernel_launches += kKernelsPerStep;
+            c->kernel_launches += kKernelsPerStep + (use_mask_passes(c) ? 1 : 0);
         } else {
             enqueue_step(c);
         }

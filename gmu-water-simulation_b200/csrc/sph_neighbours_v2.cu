@@ -62,6 +62,13 @@ __device__ __forceinline__ u64 t_exact2(u64 px, u64 py, u64 pz, u64 x, u64 y, u6
     return sub2(h2, add2(add2(fma2(dx, dx, nz), fma2(dy, dy, nz)), fma2(dz, dz, nz)));
 }
 
+// MUFU.RSQ without the denormal-rescaling wrapper rsqrtf() carries (r2 is never that small for a real pair)
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ void ld256(const float4 *p, float4 &a, float4 &b) {
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
@@ -175,7 +182,7 @@ __device__ __forceinline__ void pair_term(ForceSum &f, const float4 pi, const fl
                                           const bool self, const Params &P) {
     const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
     const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    const float inv_r = self ? 0.0f : rsqrtf(r2);
+    const float inv_r = self ? 0.0f : rsqrt_fast(r2);
     const float r = r2 * inv_r;
     const float hr = P.h - r;
     const float g = (P.spiky_f * hr) * (hr * inv_r) * (pi.w + pj.w);
@@ -188,13 +195,27 @@ __device__ __forceinline__ void pair_term(ForceSum &f, const float4 pi, const fl
     f.vz = fmaf(l, vj.z - vi.z, f.vz);
 }
 
-// Slow path for a particle whose hit words did not fit (> kMaskWords non-empty words): walk all 27
-// cells with the exact predicate, like the variant-0 kernel.
-__device__ __noinline__ void forces_overflow_path(ForceSum &f, const int i, const float4 pi, const float4 vi, const int key,
-                                                  const float *__restrict__ xs, const float *__restrict__ ys,
-                                                  const float *__restrict__ zs, const float4 *__restrict__ fdat,
-                                                  const int *__restrict__ cell_start, const Params &P) {
-    for_each_row(key, cell_start, P, [&](int a, int b) {
+// f_p *= -m rho_i ; f_v *= mu m ; a = (f_p + f_v + g rho_i) / rho_i   (src/CCPUParticleSimulator.cpp:191-195)
+__device__ __forceinline__ float4 force_result(const ForceSum &f, const float rho, const Params &P) {
+    const float sp = -P.mass * rho, sv = P.viscosity * P.mass;
+    return make_float4((f.px * sp + f.vx * sv + P.gx * rho) / rho, (f.py * sp + f.vy * sv + P.gy * rho) / rho,
+                       (f.pz * sp + f.vz * sv + P.gz * rho) / rho, 0.0f);
+}
+
+// Particles whose hit words did not fit (> kMaskWords non-empty words, extremely dense clumps) are skipped by the
+// main kernel and handled here: walk all 27 cells with the exact predicate, like the variant-0 kernel.
+__global__ void __launch_bounds__(128) k_forces_overflow(const float *__restrict__ xs, const float *__restrict__ ys,
+                                                         const float *__restrict__ zs, const float4 *__restrict__ fdat,
+                                                         const float4 *__restrict__ dp, const int *__restrict__ nb_words,
+                                                         const int *__restrict__ key, const int *__restrict__ cell_start,
+                                                         float4 *__restrict__ acc, int i0, int n,
+                                                         const __grid_constant__ Params P) {
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || __ldg(nb_words + i) <= kMaskWords) return;
+    float4 pi, vi;
+    ld256(fdat + 2 * (size_t)i, pi, vi);
+    ForceSum f = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for_each_row(__ldg(key + i), cell_start, P, [&](int a, int b) {
         for (int j = a; j < b; ++j) {
             const float r2 = r2_exact(pi.x - __ldg(xs + j), pi.y - __ldg(ys + j), pi.z - __ldg(zs + j));
             if (P.h2 - r2 >= 0.0f && j != i) {
@@ -204,59 +225,51 @@ __device__ __noinline__ void forces_overflow_path(ForceSum &f, const int i, cons
             }
         }
     });
+    acc[i] = force_result(f, __ldg(&dp[i].x), P);
 }
 
-__global__ void __launch_bounds__(128) k_forces_mask(const float *__restrict__ xs, const float *__restrict__ ys,
-                                                     const float *__restrict__ zs, const float4 *__restrict__ fdat,
-                                                     const float4 *__restrict__ dp, const uint2 *__restrict__ mask,
-                                                     const int *__restrict__ nb_words, const int *__restrict__ key,
-                                                     const int *__restrict__ cell_start, float4 *__restrict__ acc,
-                                                     int i0, int n, const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(128) k_forces_mask(const float4 *__restrict__ fdat, const float4 *__restrict__ dp,
+                                                     const uint2 *__restrict__ mask, const int *__restrict__ nb_words,
+                                                     float4 *__restrict__ acc, int i0, int n,
+                                                     const __grid_constant__ Params P) {
     const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;  // particles [i0, n): slab mode runs sub-ranges
     if (i >= n) return;
+    const int nw = __ldg(nb_words + i);
+    if (nw > kMaskWords) return;  // k_forces_overflow's job
     float4 pi, vi;
     ld256(fdat + 2 * (size_t)i, pi, vi);
     ForceSum f = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const int nw = __ldg(nb_words + i);
-    if (nw > kMaskWords) {
-        forces_overflow_path(f, i, pi, vi, __ldg(key + i), xs, ys, zs, fdat, cell_start, P);
-    } else {
-        // Flat walk: every lane consumes its own stream of set bits; a lane that runs out of bits pulls its
-        // next word (prefetched one ahead), so the warp runs for max(hits) iterations, not sum of per-word maxima.
-        const uint2 *wp = mask + ((size_t)(i >> 5) * kMaskWords) * 32 + (i & 31);
-        const uint2 *const wend = wp + (size_t)nw * 32;
-        uint2 next = nw > 0 ? __ldg(wp) : make_uint2(0u, 0u);
-        unsigned m = 0;
-        int j31 = 0;
-        for (;;) {
-            if (m == 0) {
-                if (wp == wend) break;
-                m = next.x;
-                j31 = (int)next.y;
-                wp += 32;
-                if (wp != wend) next = __ldg(wp);
-            }
-            const int msb = 31 - __clz(m);  // stored words are never empty
-            m &= ~(1u << msb);
-            const int j = j31 - msb;
-            float4 pj, vj;
-            ld256(fdat + 2 * (size_t)j, pj, vj);
-            pair_term(f, pi, vi, pj, vj, j == i, P);
+    // Flat walk: every lane consumes its own stream of set bits; a lane that runs out of bits pulls its next
+    // word (prefetched one ahead), so the warp runs for max(hits) iterations, not the sum of per-word maxima.
+    const uint2 *const wbase = mask + ((size_t)(i >> 5) * kMaskWords) * 32 + (i & 31);
+    uint2 next = nw > 0 ? __ldg(wbase) : make_uint2(0u, 0u);
+    unsigned m = 0;
+    int j31 = 0, w = 0;
+    for (;;) {
+        if (m == 0) {
+            if (w == nw) break;
+            m = next.x;
+            j31 = (int)next.y;
+            ++w;
+            if (w < nw) next = __ldg(wbase + w * 32);
         }
+        const int msb = 31 - __clz(m);  // stored words are never empty
+        m &= ~(1u << msb);
+        const int j = j31 - msb;
+        float4 pj, vj;
+        ld256(fdat + 2 * (size_t)j, pj, vj);
+        pair_term(f, pi, vi, pj, vj, j == i, P);
     }
-    // f_p *= -m rho_i ; f_v *= mu m ; a = (f_p + f_v + g rho_i) / rho_i   (src/CCPUParticleSimulator.cpp:191-195)
-    const float rho = __ldg(&dp[i].x);
-    const float sp = -P.mass * rho, sv = P.viscosity * P.mass;
-    acc[i] = make_float4((f.px * sp + f.vx * sv + P.gx * rho) / rho, (f.py * sp + f.vy * sv + P.gy * rho) / rho,
-                         (f.pz * sp + f.vz * sv + P.gz * rho) / rho, 0.0f);
+    acc[i] = force_result(f, __ldg(&dp[i].x), P);
 }
 
 void launch_forces_mask(const NbBuffers &nb, const float4 *dp, const int *nb_count, const int *key_s, const int *cell_start,
                         float4 *acc, int i0, int i1, const Params &P, cudaStream_t st) {
     if (i1 <= i0) return;
     (void)nb_count;
-    k_forces_mask<<<(i1 - i0 + 127) / 128, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, nb.fdat, dp, nb.mask, nb.words, key_s,
-                                                         cell_start, acc, i0, i1, P);
+    const int grid = (i1 - i0 + 127) / 128;
+    k_forces_mask<<<grid, 128, 0, st>>>(nb.fdat, dp, nb.mask, nb.words, acc, i0, i1, P);
+    k_forces_overflow<<<grid, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, nb.fdat, dp, nb.words, key_s, cell_start, acc, i0, i1, P);
 }
 
 }  // namespace sph
