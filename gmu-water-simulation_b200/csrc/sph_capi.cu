@@ -1055,6 +1055,7 @@ int sph_set_option(sph_context *c, const char *name, int value) {
     else if (k == "use_graph") c->opt_use_graph = value;
     else if (k == "count_neighbours") c->opt_count_neighbours = value;
     else if (k == "flush_l2") { c->opt_flush_l2 = value; return SPH_OK; }
+    else if (k == "tuning") c->P.tuning = value;
     else if (k == "slab_overlap") {
         REQUIRE(c, c->slab, SPH_ERR_STATE, "sph_set_option: slab_overlap needs a slab context");
         c->slab->opt_overlap = value;

@@ -28,6 +28,7 @@ struct Params {
     float h, h2;          // h2 = fl32(h*h) == 0x3b08df0c
     float hbx_f, hby_f, hbz_f;  // float(half box): cell-face positions for the conservative row pruning
     float prune_margin;         // slack (1e-3 h) that makes the pruning bounds safe under fp32 rounding
+    int tuning;                 // experiment switches (sph_set_option("tuning", bits)); 0 in production
     float neg_zero;             // -0.0f as a RUNTIME value: fma(d, d, -0) == fl(d*d), and ptxas cannot re-fuse it (see v2)
     float dt;
     float mass, viscosity, gas_stiffness, rest_density;
@@ -59,6 +60,31 @@ __device__ __forceinline__ int cell_key(float4 p, const Params &P) {
     int cz = cell_coord(p.z, P.hbz, P.h_d, P.rz_global) - P.z_base;
     cz = min(max(cz, 0), P.rz - 1);
     return cx + cy * P.rx + cz * P.rx * P.ry;
+}
+
+// Same enumeration, but the callback also gets the row slot (dz+1)*3 + (dy+1) in 0..8.
+template <typename F>
+__device__ __forceinline__ void for_each_row_slot(int key, const int *__restrict__ cell_start, const Params &P, F &&f) {
+    const int rxy = P.rx * P.ry;
+    const int cz = key / rxy;
+    const int rem = key - cz * rxy;
+    const int cy = rem / P.rx;
+    const int cx = rem - cy * P.rx;
+    const int xl = max(cx - 1, 0), xr = min(cx + 1, P.rx - 1);
+#pragma unroll 1
+    for (int dz = -1; dz <= 1; ++dz) {
+        const int z = cz + dz;
+        if (z < 0 || z >= P.rz) continue;
+#pragma unroll 1
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int y = cy + dy;
+            if (y < 0 || y >= P.ry) continue;
+            const int c0 = xl + y * P.rx + z * rxy;
+            const int a = __ldg(cell_start + c0);
+            const int b = __ldg(cell_start + c0 + (xr - xl) + 1);
+            f((dz + 1) * 3 + (dy + 1), a, b);
+        }
+    }
 }
 
 // Up to 9 contiguous candidate ranges (x-1..x+1 merged because x is the fastest cell axis).

@@ -6,7 +6,7 @@
 // the permutation and every later summation order are pure functions of the particle state.
 //
 //   K1 cell_key_hist : key[i] = cell(pos[i]) in fp64, off[i] = atomicAdd(count[key], 1)
-//   K2 scan          : single-pass decoupled look-back exclusive scan of count -> cell_start,
+//   K2 scan          : single-pass decoupled look-back exclusive scan of count -> cell_start (8192 cells per tile),
 //                      zeroes count for the next step
 //   K3 bucket        : slot = cell_start[key] + off  ->  bucket_src/bucket_id   (arrival order)
 //   K4 rank_scatter  : rank inside the cell by particle id, gather pos/vel into canonical order
@@ -53,12 +53,17 @@ __global__ void __launch_bounds__(512) k_scan(int *__restrict__ count, int *__re
     if (tid == 0) s_tile = (int)atomicAdd(status + n_tiles, 1ull);  // ticket: tiles start in order
     __syncthreads();
     const int tile = s_tile;
-    const int base = tile * kScanTile + tid * 4;
+    const int base = tile * kScanTile + tid * (4 * kScanVec);
 
     // buffers are padded to a multiple of the tile and the padding stays zero
-    int4 c = *reinterpret_cast<const int4 *>(count + base);
-    *reinterpret_cast<int4 *>(count + base) = make_int4(0, 0, 0, 0);
-    const int t_sum = c.x + c.y + c.z + c.w;
+    int4 c[kScanVec];
+    int t_sum = 0;
+#pragma unroll
+    for (int v = 0; v < kScanVec; ++v) {
+        c[v] = *reinterpret_cast<const int4 *>(count + base + 4 * v);
+        *reinterpret_cast<int4 *>(count + base + 4 * v) = make_int4(0, 0, 0, 0);
+        t_sum += c[v].x + c[v].y + c[v].z + c[v].w;
+    }
 
     int incl = t_sum;
 #pragma unroll
@@ -111,13 +116,17 @@ __global__ void __launch_bounds__(512) k_scan(int *__restrict__ count, int *__re
         if (lane == 0) s_prefix = prefix;
     }
     __syncthreads();
-    const int e = s_prefix + thread_excl;
-    int4 o;
-    o.x = e;
-    o.y = e + c.x;
-    o.z = o.y + c.y;
-    o.w = o.z + c.z;
-    *reinterpret_cast<int4 *>(cell_start + base) = o;
+    int e = s_prefix + thread_excl;
+#pragma unroll
+    for (int v = 0; v < kScanVec; ++v) {
+        int4 o;
+        o.x = e;
+        o.y = e + c[v].x;
+        o.z = o.y + c[v].y;
+        o.w = o.z + c[v].z;
+        e = o.w + c[v].w;
+        *reinterpret_cast<int4 *>(cell_start + base + 4 * v) = o;
+    }
     (void)n_items;
 }
 

@@ -5,7 +5,8 @@
 
 namespace sph {
 
-constexpr int kScanTile = 2048;  // cells per scan tile (512 threads x int4)
+constexpr int kScanVec = 4;                    // int4 vectors per thread in the scan
+constexpr int kScanTile = 512 * 4 * kScanVec;  // cells per scan tile (512 threads x 4 x int4 = 8192): short look-back chains
 constexpr int kMaskWords = 32;   // stored (non-empty) hit words per particle; more -> overflow path
 constexpr int kSoaPad = 64;      // far-away sentinel entries after the last particle of xs/ys/zs
 

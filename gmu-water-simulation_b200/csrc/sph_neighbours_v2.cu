@@ -75,9 +75,42 @@ __device__ __forceinline__ void ld256(const float4 *p, float4 &a, float4 &b) {
         : "l"(p));
 }
 
+// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) -------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+constexpr int kStageCap = 256;  // candidates staged per row slot; longer unions fall back to global loads
+
 // ================================================================= density + pressure + hit bitmask
 // Word format: bit 31 = first candidate of the word (index j0), bit 31-k = candidate j0+k.
 // Stored as uint2 {bits, j0 + 31} so that the force pass gets j = (j0 + 31) - msb_index(bits).
+// STAGED: the <= 9 row unions this CTA's 128 consecutive particles can touch are first copied into shared memory
+// with 1-D bulk async copies (one thread per row slot issues three copies, an mbarrier collects the bytes);
+// the candidate loads of the scan are then LDS.128 instead of LDG.128.
+template <bool STAGED>
 __global__ void __launch_bounds__(128, 8) k_density_mask(const float *__restrict__ xs, const float *__restrict__ ys,
                                                       const float *__restrict__ zs, const float4 *__restrict__ vel,
                                                       const int *__restrict__ key, const int *__restrict__ cell_start,
@@ -86,25 +119,67 @@ __global__ void __launch_bounds__(128, 8) k_density_mask(const float *__restrict
                                                       int *__restrict__ nb_words, int n,
                                                       const __grid_constant__ Params P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ __align__(16) float s_x[STAGED ? 9 : 1][STAGED ? kStageCap + 8 : 4];
+    __shared__ __align__(16) float s_y[STAGED ? 9 : 1][STAGED ? kStageCap + 8 : 4];
+    __shared__ __align__(16) float s_z[STAGED ? 9 : 1][STAGED ? kStageCap + 8 : 4];
+    __shared__ int s_base[9], s_cnt[9];  // first staged index of the slot; staged count (0: fall back to global)
+    __shared__ unsigned long long s_bar;
+    if (STAGED) {
+        if (threadIdx.x == 0) mbar_init(&s_bar, 9);
+        __syncthreads();
+        if (threadIdx.x < 9) {
+            const int slot = threadIdx.x;
+            const int p0 = blockIdx.x * blockDim.x, p1 = min(p0 + (int)blockDim.x, n) - 1;
+            const int off = (slot % 3 - 1) * P.rx + (slot / 3 - 1) * P.rx * P.ry;
+            const int lo = max(__ldg(key + p0) + off - 1, 0), hi = min(__ldg(key + p1) + off + 1, P.n_cells - 1);
+            int base = 0, cnt = 0;
+            if (lo <= hi) {
+                base = __ldg(cell_start + lo) & ~3;
+                cnt = ((__ldg(cell_start + hi + 1) - base + 3) & ~3) + 4;  // + the <= 3 over-scanned slots
+                if (cnt > kStageCap + 8) cnt = 0;
+            }
+            s_base[slot] = base;
+            s_cnt[slot] = cnt;
+            if (cnt > 0) {
+                mbar_arrive_expect_tx(&s_bar, 3u * 4u * (unsigned)cnt);
+                bulk_g2s(s_x[slot], xs + base, 4u * (unsigned)cnt, &s_bar);
+                bulk_g2s(s_y[slot], ys + base, 4u * (unsigned)cnt, &s_bar);
+                bulk_g2s(s_z[slot], zs + base, 4u * (unsigned)cnt, &s_bar);
+            } else {
+                mbar_arrive_expect_tx(&s_bar, 0u);
+            }
+        }
+        __syncthreads();  // s_base / s_cnt visible
+    }
     if (i >= n) return;
     const float px = __ldg(xs + i), py = __ldg(ys + i), pz = __ldg(zs + i);
     const u64 px2 = pk(px, px), py2 = pk(py, py), pz2 = pk(pz, pz), h22 = pk(P.h2, P.h2);
     const u64 nz2 = pk(P.neg_zero, P.neg_zero);
     uint2 *const wbase = mask + ((size_t)(i >> 5) * kMaskWords) * 32 + (i & 31);
+    if (STAGED) mbar_wait(&s_bar, 0);
     u64 sum_a = 0ull, sum_b = 0ull;  // two packed accumulators (+0.0f, +0.0f)
     float stray_sum = 0.0f;
     int cnt = 0, widx = 0;
-    for_each_row(__ldg(key + i), cell_start, P, [&](const int a, const int b) {
+    for_each_row_slot(__ldg(key + i), cell_start, P, [&](const int slot, const int a, const int b) {
         int j = a & ~3;
+        const bool staged = STAGED && s_cnt[slot] > 0;
+        const int sbase = STAGED ? s_base[slot] : 0;
         while (j < b) {
             const int jw = j;
             const int jend = min(jw + 32, b);
             unsigned miss = 0;  // sign bits of t, first candidate ends up in the highest bit shifted in
 #pragma unroll 2
             for (; j < jend; j += 4) {
-                const ulonglong2 X = __ldg(reinterpret_cast<const ulonglong2 *>(xs + j));
-                const ulonglong2 Y = __ldg(reinterpret_cast<const ulonglong2 *>(ys + j));
-                const ulonglong2 Z = __ldg(reinterpret_cast<const ulonglong2 *>(zs + j));
+                ulonglong2 X, Y, Z;
+                if (staged) {
+                    X = *reinterpret_cast<const ulonglong2 *>(&s_x[STAGED ? slot : 0][j - sbase]);
+                    Y = *reinterpret_cast<const ulonglong2 *>(&s_y[STAGED ? slot : 0][j - sbase]);
+                    Z = *reinterpret_cast<const ulonglong2 *>(&s_z[STAGED ? slot : 0][j - sbase]);
+                } else {
+                    X = __ldg(reinterpret_cast<const ulonglong2 *>(xs + j));
+                    Y = __ldg(reinterpret_cast<const ulonglong2 *>(ys + j));
+                    Z = __ldg(reinterpret_cast<const ulonglong2 *>(zs + j));
+                }
                 const u64 t01 = t_exact2(px2, py2, pz2, X.x, Y.x, Z.x, h22, nz2);
                 const u64 t23 = t_exact2(px2, py2, pz2, X.y, Y.y, Z.y, h22, nz2);
                 float t0, t1, t2, t3;
@@ -156,19 +231,23 @@ __global__ void __launch_bounds__(128, 8) k_density_mask(const float *__restrict
     const float prs = P.gas_stiffness * (rho - P.rest_density);
     const float inv_rho = 1.0f / rho;
     const float A = prs * inv_rho * inv_rho;
-    dp[i] = make_float4(rho, prs, A, inv_rho);
+    __stcs(dp + i, make_float4(rho, prs, A, inv_rho));
     const float4 v = __ldg(vel + i);
-    fdat[2 * (size_t)i] = make_float4(px, py, pz, A);
-    fdat[2 * (size_t)i + 1] = make_float4(v.x, v.y, v.z, inv_rho);
-    nb_count[i] = cnt;
-    nb_words[i] = widx;  // > kMaskWords: the force pass takes the overflow path for this particle
+    __stcs(fdat + 2 * (size_t)i, make_float4(px, py, pz, A));
+    __stcs(fdat + 2 * (size_t)i + 1, make_float4(v.x, v.y, v.z, inv_rho));
+    __stcs(nb_count + i, cnt);
+    __stcs(nb_words + i, widx);  // > kMaskWords: the force pass takes the overflow path for this particle
 }
 
 void launch_density_mask(const NbBuffers &nb, const float4 *vel_s, const int *key_s, const int *cell_start, float4 *dp,
                          int *nb_count, int n, const Params &P, cudaStream_t st) {
     if (n <= 0) return;
-    k_density_mask<<<(n + 127) / 128, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, vel_s, key_s, cell_start, dp, nb.fdat, nb.mask,
-                                                    nb_count, nb.words, n, P);
+    if (P.tuning & 2)
+        k_density_mask<true><<<(n + 127) / 128, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, vel_s, key_s, cell_start, dp, nb.fdat,
+                                                              nb.mask, nb_count, nb.words, n, P);
+    else
+        k_density_mask<false><<<(n + 127) / 128, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, vel_s, key_s, cell_start, dp, nb.fdat,
+                                                               nb.mask, nb_count, nb.words, n, P);
 }
 
 // ================================================================= forces from the bitmask
@@ -228,6 +307,7 @@ __global__ void __launch_bounds__(128) k_forces_overflow(const float *__restrict
     acc[i] = force_result(f, __ldg(&dp[i].x), P);
 }
 
+template <int HITS>  // HITS neighbours per loop iteration (their gathers are all in flight before the first pair term)
 __global__ void __launch_bounds__(128) k_forces_mask(const float4 *__restrict__ fdat, const float4 *__restrict__ dp,
                                                      const uint2 *__restrict__ mask, const int *__restrict__ nb_words,
                                                      float4 *__restrict__ acc, int i0, int n,
@@ -253,12 +333,22 @@ __global__ void __launch_bounds__(128) k_forces_mask(const float4 *__restrict__ 
             ++w;
             if (w < nw) next = __ldg(wbase + w * 32);
         }
-        const int msb = 31 - __clz(m);  // stored words are never empty
-        m &= ~(1u << msb);
-        const int j = j31 - msb;
-        float4 pj, vj;
-        ld256(fdat + 2 * (size_t)j, pj, vj);
-        pair_term(f, pi, vi, pj, vj, j == i, P);
+        int j[HITS];
+        float4 pj[HITS], vj[HITS];
+#pragma unroll
+        for (int k = 0; k < HITS; ++k) {
+            // further hits come from the same word; when it has run dry the slot re-reads the particle's own
+            // record, which contributes exactly 0
+            j[k] = i;
+            if (k == 0 || m) {
+                const int msb = 31 - __clz(m);
+                m &= ~(1u << msb);
+                j[k] = j31 - msb;
+            }
+            ld256(fdat + 2 * (size_t)j[k], pj[k], vj[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < HITS; ++k) pair_term(f, pi, vi, pj[k], vj[k], j[k] == i, P);
     }
     acc[i] = force_result(f, __ldg(&dp[i].x), P);
 }
@@ -268,7 +358,10 @@ void launch_forces_mask(const NbBuffers &nb, const float4 *dp, const int *nb_cou
     if (i1 <= i0) return;
     (void)nb_count;
     const int grid = (i1 - i0 + 127) / 128;
-    k_forces_mask<<<grid, 128, 0, st>>>(nb.fdat, dp, nb.mask, nb.words, acc, i0, i1, P);
+    if (P.tuning & 1)
+        k_forces_mask<2><<<grid, 128, 0, st>>>(nb.fdat, dp, nb.mask, nb.words, acc, i0, i1, P);
+    else
+        k_forces_mask<1><<<grid, 128, 0, st>>>(nb.fdat, dp, nb.mask, nb.words, acc, i0, i1, P);
     k_forces_overflow<<<grid, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, nb.fdat, dp, nb.words, key_s, cell_start, acc, i0, i1, P);
 }
 

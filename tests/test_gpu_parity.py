@@ -27,6 +27,8 @@ def state_after(box, steps, scenario=DAM_BREAK):
 def make_ctx(gws, box, pos, vel, cap=None, variant=1):
     ctx = gws.SphContext(box, cap or max(len(pos), 1))
     ctx.set_option("neighbour_variant", variant)  # 1 = bitmask passes (production), 0 = plain float4 walk
+    if os.environ.get("SPH_TUNING"):
+        ctx.set_option("tuning", int(os.environ["SPH_TUNING"]))  # experiment switches of the kernels under test
     ctx.upload(gws.particles_from_arrays(pos, vel))
     return ctx
 

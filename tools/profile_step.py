@@ -12,11 +12,13 @@ ap.add_argument("--box", type=float, default=3.62)
 ap.add_argument("--preroll", type=int, default=200)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--neighbour-variant", type=int, default=1)
+ap.add_argument("--tuning", type=int, default=0)
 a = ap.parse_args()
 sim = gws.Simulator("cuda", a.box).setup_scene()
 ctx = sim.context()
 ctx.set_option("use_graph", 0)
 ctx.set_option("neighbour_variant", a.neighbour_variant)
+ctx.set_option("tuning", a.tuning)
 for _ in range(a.preroll):
     ctx.step(1, timed=False)
 ctx.synchronize()
