@@ -380,3 +380,63 @@ def test_fountain_at_scale_with_nozzle_array(gws):
     ctx.update_grid(); ctx.density_pressure()
     counts, _ = ctx.neighbours(lists=False)
     assert counts.min() >= 1 and hp["density"].max() > 328.0
+
+
+@pytest.mark.parametrize("seed,n,box", [(0xC0FFEE, 6000, 0.5), (7, 2500, (0.6, 0.25, 0.4)), (99, 4000, 0.4)])
+def test_random_states_with_awkward_particles(gws, seed, n, box):
+    """Seeded random clouds instead of lattice-born states: non-uniform density, particles outside the box
+    (clamped into edge cells like the reference does), particles exactly on cell faces and box walls, duplicated
+    x/y/z coordinates, and non-contiguous ids in shuffled upload order."""
+    rng = np.random.default_rng(seed)
+    b = np.array([box] * 3 if np.isscalar(box) else box, dtype=np.float32)
+    pos = ((rng.random((n, 3), dtype=np.float32) - 0.5) * b * np.float32(0.9)).astype(np.float32)
+    pos[: n // 4] *= np.float32(0.35)                                   # a dense core (60+ neighbours)
+    h = np.float32(0.0457)
+    k = n // 10
+    # x and z snapped to multiples of h (cell faces when b/2 is a multiple of h, generic otherwise); y stays random so
+    # that no two particles coincide (r = 0 gives 0/0 = NaN in the reference as well)
+    pos[n // 2:n // 2 + k, 0::2] = (np.floor(pos[n // 2:n // 2 + k, 0::2] / h) * h).astype(np.float32)
+    pos[-40:-20] = (pos[-40:-20] + np.sign(pos[-40:-20]) * b).astype(np.float32)               # outside the box
+    pos[-20:-10, 0] = -b[0] / 2                                          # exactly on the left wall
+    pos[-10:, 1] = pos[-11, 1]                                           # shared y coordinate
+    vel = ((rng.random((n, 3), dtype=np.float32) - 0.5) * np.float32(2.0)).astype(np.float32)
+    o = Oracle(tuple(float(v) for v in b)).set_state(pos, vel)
+    ids = rng.permutation(n)                                             # upload order != id order
+    ctx = gws.SphContext(tuple(float(v) for v in b), n)
+    ctx.upload(gws.particles_from_arrays(pos[ids], vel[ids], ids=ids))
+    o.update_grid(); ctx.update_grid()
+    assert np.array_equal(ctx.keys(), o.keys())
+    cs, perm = o.cells()
+    assert np.array_equal(ctx.cell_start(), cs) and np.array_equal(ctx.permutation().astype(np.int32), perm)
+    o.update_density_pressure(); ctx.density_pressure()
+    oc, ol = o.neighbours(); gc, gl = ctx.neighbours()
+    assert np.array_equal(gc, oc) and np.array_equal(gl, ol)
+    rho, prs, _ = ctx.density_pressure_accel()
+    check_density(o, rho, prs)
+    o.update_forces(); ctx.forces()
+    assert np.isfinite(o.acc).all()
+    check_acc(o.acc_sph, o.acc_scale, ctx.density_pressure_accel()[2])
+    ctx.integrate()
+    acc_tot = ctx.density_pressure_accel()[2]
+    check_acc(o.acc, o.acc_scale, acc_tot)
+    rec = ctx.download()
+    tol = pos_tolerance(o)
+    o.integrate()
+    assert np.all(np.abs(rec["position"][:, :3] - o.pos) <= tol)
+
+
+def test_headless_cpp_bench_runs(gws):
+    """core/sph_bench (the headless C++ driver of the reference-facing simulator) on the small dam break."""
+    import json
+    import subprocess
+
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gmu-water-simulation_b200", "sph_bench")
+    out = subprocess.run([exe, "--box", "0.9", "--steps", "50", "--warmup", "5"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["particles"] == 16000 and line["particle_steps_per_s"] > 1e6
+    out = subprocess.run([exe, "--box", "0.4", "--scenario", "fountain", "--steps", "30", "--warmup", "0", "--phases"],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["particles"] == 210 and line["phase_ms"]["density"] > 0 and line["phase_ms"]["collisions"] == 0
