@@ -698,6 +698,7 @@ int sph_append_particles(sph_context *c, const sph_particle *aos, uint32_t n_new
 int sph_download_particles(sph_context *c, sph_particle *aos, uint32_t capacity, uint32_t *n_out) {
     REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
     REQUIRE(c, aos && capacity >= c->n, SPH_ERR_ARGUMENT, "sph_download_particles: buffer too small");
+    REQUIRE(c, !c->slab, SPH_ERR_STATE, "sph_download_particles: indexed by global id - not available in slab mode (use sph_download_owned)");
     CUDA_TRY(c, cudaSetDevice(c->device));
     const bool aux = aux_aligned(c);
     for (uint32_t base = 0; base < c->n;) {
@@ -885,6 +886,7 @@ int sph_synchronize(sph_context *c) {
 int sph_download_keys(sph_context *c, int32_t *keys) {
     REQUIRE(c, c && keys, SPH_ERR_ARGUMENT, "sph_download_keys: NULL argument");
     REQUIRE(c, c->grid_valid, SPH_ERR_STATE, "sph_download_keys: grid not built");
+    REQUIRE(c, !c->slab, SPH_ERR_STATE, "sph_download_keys: indexed by global id - not available in slab mode (use sph_download_owned)");
     CUDA_TRY(c, cudaSetDevice(c->device));
     launch_scatter_by_id_i32(c->pos_s, c->g.key_s, c->d_tmp_i32, (int)c->n, c->stream);
     c->kernel_launches += 1;
@@ -896,6 +898,7 @@ int sph_download_keys(sph_context *c, int32_t *keys) {
 int sph_download_permutation(sph_context *c, uint32_t *sorted_ids) {
     REQUIRE(c, c && sorted_ids, SPH_ERR_ARGUMENT, "sph_download_permutation: NULL argument");
     REQUIRE(c, c->grid_valid, SPH_ERR_STATE, "sph_download_permutation: grid not built");
+    REQUIRE(c, !c->slab, SPH_ERR_STATE, "sph_download_permutation: indexed by global id - not available in slab mode (use sph_download_owned)");
     CUDA_TRY(c, cudaSetDevice(c->device));
     launch_extract_ids(c->pos_s, reinterpret_cast<unsigned *>(c->d_tmp_i32), (int)c->n, c->stream);
     c->kernel_launches += 1;
@@ -917,6 +920,7 @@ int sph_download_cell_start(sph_context *c, int32_t *cell_start) {
 int sph_download_density_pressure_accel(sph_context *c, float *density, float *pressure, float *accel3) {
     REQUIRE(c, c && density && pressure && accel3, SPH_ERR_ARGUMENT, "sph_download_density_pressure_accel: NULL argument");
     REQUIRE(c, c->s_valid && c->density_valid, SPH_ERR_STATE, "sph_download_density_pressure_accel: nothing computed yet");
+    REQUIRE(c, !c->slab, SPH_ERR_STATE, "sph_download_density_pressure_accel: indexed by global id - not available in slab mode (use sph_download_owned)");
     CUDA_TRY(c, cudaSetDevice(c->device));
     const size_t n = c->n;
     float *rho = c->d_tmp_f32, *prs = rho + n, *a3 = prs + n;
@@ -932,6 +936,7 @@ int sph_download_density_pressure_accel(sph_context *c, float *density, float *p
 int sph_download_neighbours(sph_context *c, int32_t *counts, int32_t *lists, uint64_t lists_capacity, uint64_t *total) {
     REQUIRE(c, c && counts, SPH_ERR_ARGUMENT, "sph_download_neighbours: NULL argument");
     REQUIRE(c, c->grid_valid && c->density_valid, SPH_ERR_STATE, "sph_download_neighbours: run sph_density_pressure first");
+    REQUIRE(c, !c->slab, SPH_ERR_STATE, "sph_download_neighbours: indexed by global id - not available in slab mode (use sph_download_owned)");
     CUDA_TRY(c, cudaSetDevice(c->device));
     const size_t n = c->n;
     launch_scatter_by_id_i32(c->pos_s, c->nb_count, c->d_tmp_i32, (int)n, c->stream);
@@ -1005,6 +1010,7 @@ int sph_brute_forces(sph_context *c, double *ms) {
 int sph_brute_neighbour_counts(sph_context *c, int32_t *counts) {
     REQUIRE(c, c && counts, SPH_ERR_ARGUMENT, "sph_brute_neighbour_counts: NULL argument");
     REQUIRE(c, c->s_valid && c->density_valid, SPH_ERR_STATE, "sph_brute_neighbour_counts: density first");
+    REQUIRE(c, !c->slab, SPH_ERR_STATE, "sph_brute_neighbour_counts: indexed by global id - not available in slab mode (use sph_download_owned)");
     CUDA_TRY(c, cudaSetDevice(c->device));
     launch_scatter_by_id_i32(c->pos_s, c->nb_count, c->d_tmp_i32, (int)c->n, c->stream);
     c->kernel_launches += 1;

@@ -307,7 +307,6 @@ __global__ void __launch_bounds__(128) k_forces_overflow(const float *__restrict
     acc[i] = force_result(f, __ldg(&dp[i].x), P);
 }
 
-template <int HITS>  // HITS neighbours per loop iteration (their gathers are all in flight before the first pair term)
 __global__ void __launch_bounds__(128) k_forces_mask(const float4 *__restrict__ fdat, const float4 *__restrict__ dp,
                                                      const uint2 *__restrict__ mask, const int *__restrict__ nb_words,
                                                      float4 *__restrict__ acc, int i0, int n,
@@ -333,22 +332,12 @@ __global__ void __launch_bounds__(128) k_forces_mask(const float4 *__restrict__ 
             ++w;
             if (w < nw) next = __ldg(wbase + w * 32);
         }
-        int j[HITS];
-        float4 pj[HITS], vj[HITS];
-#pragma unroll
-        for (int k = 0; k < HITS; ++k) {
-            // further hits come from the same word; when it has run dry the slot re-reads the particle's own
-            // record, which contributes exactly 0
-            j[k] = i;
-            if (k == 0 || m) {
-                const int msb = 31 - __clz(m);
-                m &= ~(1u << msb);
-                j[k] = j31 - msb;
-            }
-            ld256(fdat + 2 * (size_t)j[k], pj[k], vj[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < HITS; ++k) pair_term(f, pi, vi, pj[k], vj[k], j[k] == i, P);
+        const int msb = 31 - __clz(m);  // stored words are never empty
+        m &= ~(1u << msb);
+        const int j = j31 - msb;
+        float4 pj, vj;
+        ld256(fdat + 2 * (size_t)j, pj, vj);
+        pair_term(f, pi, vi, pj, vj, j == i, P);
     }
     acc[i] = force_result(f, __ldg(&dp[i].x), P);
 }
@@ -358,10 +347,7 @@ void launch_forces_mask(const NbBuffers &nb, const float4 *dp, const int *nb_cou
     if (i1 <= i0) return;
     (void)nb_count;
     const int grid = (i1 - i0 + 127) / 128;
-    if (P.tuning & 1)
-        k_forces_mask<2><<<grid, 128, 0, st>>>(nb.fdat, dp, nb.mask, nb.words, acc, i0, i1, P);
-    else
-        k_forces_mask<1><<<grid, 128, 0, st>>>(nb.fdat, dp, nb.mask, nb.words, acc, i0, i1, P);
+    k_forces_mask<<<grid, 128, 0, st>>>(nb.fdat, dp, nb.mask, nb.words, acc, i0, i1, P);
     k_forces_overflow<<<grid, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, nb.fdat, dp, nb.words, key_s, cell_start, acc, i0, i1, P);
 }
 
