@@ -52,7 +52,7 @@ struct sph_context {
     cudaGraphExec_t graph_exec = nullptr;
     uint32_t graph_n = 0;
     uint32_t last_step_n = 0xffffffffu;
-    int opt_neighbour_variant = 1, opt_use_graph = 1, opt_count_neighbours = 1;
+    int opt_neighbour_variant = 1, opt_use_graph = 1, opt_count_neighbours = 1, opt_fuse_integrate = 1;
     uint64_t kernel_launches = 0, graph_launches = 0, steps = 0;
     std::string err;
     void *pinned_ptr = nullptr;
@@ -216,8 +216,16 @@ void enqueue_integrate(sph_context *c) {
 void enqueue_step(sph_context *c) {
     enqueue_grid(c);
     enqueue_density(c);
-    enqueue_forces(c);
-    enqueue_integrate(c);
+    if (use_mask_passes(c) && c->opt_fuse_integrate) {
+        // forces + walls + integration in one kernel (plus the normally idle overflow kernel)
+        launch_forces_mask(c->nb, c->dp, c->nb_count, c->g.key_s, c->g.cell_start, c->acc, 0, (int)c->n, c->P, c->stream,
+                           c->pos_s, c->pos_a, c->vel_a);
+        c->kernel_launches += 2;
+        c->in_off = 0;
+    } else {
+        enqueue_forces(c);
+        enqueue_integrate(c);
+    }
 }
 constexpr int kKernelsPerStep = 7;
 
@@ -560,7 +568,7 @@ int sph_destroy(sph_context *c) {
     drop_graph(c);
     void *ptrs[] = {c->pos_a, c->vel_a, c->pos_s, c->vel_s, c->dp, c->acc, c->nb_count, c->g.key_a, c->g.off_a,
                     c->g.bucket_src, c->g.bucket_id, c->g.key_s, c->g.count, c->g.cell_start, c->g.scan_status,
-                    c->d_stage, c->d_tmp_i32, c->d_tmp_f32, c->d_stats, c->nb.xs, c->nb.ys, c->nb.zs, c->nb.fdat, c->nb.mask, c->nb.words};
+                    c->d_stage, c->d_tmp_i32, c->d_tmp_f32, c->d_stats, c->nb.xs, c->nb.ys, c->nb.zs, c->nb.fdat, c->nb.mask, c->nb.words, c->nb.ovf};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->d_flush) cudaFree(c->d_flush);
@@ -635,6 +643,7 @@ int sph_create(const sph_config *cfg, sph_context **out) {
     CTX_TRY(dalloc(&c->nb.fdat, 2 * cap));
     CTX_TRY(dalloc(&c->nb.mask, ((cap + 31) / 32) * (size_t)kMaskWords * 32));
     CTX_TRY(dalloc(&c->nb.words, cap));
+    CTX_TRY(dalloc(&c->nb.ovf, cap + 1));
     CTX_TRY(dalloc(&c->d_tmp_i32, cap));
     CTX_TRY(dalloc(&c->d_tmp_f32, cap * 5));
     CTX_TRY(dalloc(&c->d_stats, (size_t)8));
@@ -838,7 +847,7 @@ int sph_step(sph_context *c, int n_steps, double *ms) {
             if (c->graph_exec) {
                 CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, c->stream));
                 c->graph_launches += 1;
-                c->kernel_launches += kKernelsPerStep + (use_mask_passes(c) ? 1 : 0);
+                c->kernel_launches += kKernelsPerStep + ((use_mask_passes(c) && !c->opt_fuse_integrate) ? 1 : 0);
             } else {
                 enqueue_step(c);
             }
@@ -864,7 +873,7 @@ int sph_step(sph_context *c, int n_steps, double *ms) {
         if (c->graph_exec) {
             CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, c->stream));
             c->graph_launches += 1;
-            c->kernel_launches += kKernelsPerStep + (use_mask_passes(c) ? 1 : 0);
+            c->kernel_launches += kKernelsPerStep + ((use_mask_passes(c) && !c->opt_fuse_integrate) ? 1 : 0);
         } else {
             enqueue_step(c);
         }
@@ -1059,6 +1068,7 @@ int sph_set_option(sph_context *c, const char *name, int value) {
     const std::string k(name);
     if (k == "neighbour_variant") c->opt_neighbour_variant = value;
     else if (k == "use_graph") c->opt_use_graph = value;
+    else if (k == "fuse_integrate") c->opt_fuse_integrate = value;
     else if (k == "count_neighbours") c->opt_count_neighbours = value;
     else if (k == "flush_l2") { c->opt_flush_l2 = value; return SPH_OK; }
     else if (k == "tuning") c->P.tuning = value;
@@ -1078,6 +1088,11 @@ int sph_get_counter(const sph_context *c, const char *name, uint64_t *value) {
     if (k == "kernel_launches") *value = c->kernel_launches;
     else if (k == "graph_launches") *value = c->graph_launches;
     else if (k == "steps") *value = c->steps;
+    else if (k == "overflow_particles") {  // particles of the last density pass whose hit words did not fit
+        int v = 0;
+        cudaMemcpy(&v, c->nb.ovf, sizeof(int), cudaMemcpyDeviceToHost);
+        *value = (uint64_t)v;
+    }
     else if (k == "slab_far_movers") {  // particles that crossed more than 2 z-layers in one step (must stay 0)
         int v = 0;
         if (c->slab) cudaMemcpy(&v, c->slab->d_counters + 4, sizeof(int), cudaMemcpyDeviceToHost);

@@ -113,4 +113,47 @@ __device__ __forceinline__ void for_each_row(int key, const int *__restrict__ ce
     }
 }
 
+// ---- walls + integration, shared by k_integrate_collide and the fused force kernel -------------------
+__device__ __forceinline__ float dot_exact(float ax, float ay, float az, float bx, float by, float bz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+}
+
+// Wall penalty force exactly as the CPU path computes it (fp32 vectors, fp64 scalar d, accumulator from 0;
+// src/CCollisionGeometry.cpp:117-133) added to the SPH acceleration `a`, then x' = (x + v dt) + (a dt) dt and
+// v' = (x' - x)/dt with one rounding per operation (src/CCPUParticleSimulator.cpp:220-221).
+__device__ __forceinline__ void walls_and_integrate(const float4 p, const float4 v, float4 &a, float4 &np, float4 &nv,
+                                                    const Params &P) {
+    float wx = 0.f, wy = 0.f, wz = 0.f;
+#pragma unroll
+    for (int w = 0; w < 6; ++w) {
+        if (w >= P.wall_count) break;
+        const WallDev W = P.walls[w];
+        const float inx = __fmul_rn(W.nx, -1.0f), iny = __fmul_rn(W.ny, -1.0f), inz = __fmul_rn(W.nz, -1.0f);
+        const double d = __dadd_rn((double)dot_exact(__fsub_rn(W.px, p.x), __fsub_rn(W.py, p.y), __fsub_rn(W.pz, p.z), inx, iny, inz),
+                                   P.wall_skin_d);
+        if (d > 0.0) {
+            const float df = (float)d;
+            wx = __fadd_rn(wx, __fmul_rn(__fmul_rn(P.wall_k_f, inx), df));
+            wy = __fadd_rn(wy, __fmul_rn(__fmul_rn(P.wall_k_f, iny), df));
+            wz = __fadd_rn(wz, __fmul_rn(__fmul_rn(P.wall_k_f, inz), df));
+            const float s = (float)__dmul_rn(P.wall_damping_d, (double)dot_exact(v.x, v.y, v.z, inx, iny, inz));
+            wx = __fadd_rn(wx, __fmul_rn(s, inx));
+            wy = __fadd_rn(wy, __fmul_rn(s, iny));
+            wz = __fadd_rn(wz, __fmul_rn(s, inz));
+        }
+    }
+    a.x = __fadd_rn(a.x, wx);
+    a.y = __fadd_rn(a.y, wy);
+    a.z = __fadd_rn(a.z, wz);
+    const float dt = P.dt;
+    np.x = __fadd_rn(__fadd_rn(p.x, __fmul_rn(v.x, dt)), __fmul_rn(__fmul_rn(a.x, dt), dt));
+    np.y = __fadd_rn(__fadd_rn(p.y, __fmul_rn(v.y, dt)), __fmul_rn(__fmul_rn(a.y, dt), dt));
+    np.z = __fadd_rn(__fadd_rn(p.z, __fmul_rn(v.z, dt)), __fmul_rn(__fmul_rn(a.z, dt), dt));
+    np.w = p.w;
+    nv.x = __fdiv_rn(__fsub_rn(np.x, p.x), dt);
+    nv.y = __fdiv_rn(__fsub_rn(np.y, p.y), dt);
+    nv.z = __fdiv_rn(__fsub_rn(np.z, p.z), dt);
+    nv.w = 0.0f;
+}
+
 }  // namespace sph

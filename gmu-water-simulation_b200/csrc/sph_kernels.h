@@ -7,7 +7,7 @@ namespace sph {
 
 constexpr int kScanVec = 4;                    // int4 vectors per thread in the scan
 constexpr int kScanTile = 512 * 4 * kScanVec;  // cells per scan tile (512 threads x 4 x int4 = 8192): short look-back chains
-constexpr int kMaskWords = 32;   // stored (non-empty) hit words per particle; more -> overflow path
+constexpr int kMaskWords = 40;   // stored (non-empty) hit words per particle; more -> overflow path (warp per particle)
 constexpr int kSoaPad = 64;      // far-away sentinel entries after the last particle of xs/ys/zs
 
 // Extra arrays of the production neighbour passes (sph_neighbours_v2.cu)
@@ -17,6 +17,7 @@ struct NbBuffers {
     uint2 *mask;          // [ceil(cap/32)*kMaskWords*32] hit words {bits, first candidate + 31}, warp-transposed:
                           // word w of lane l of warp q at (q*kMaskWords + w)*32 + l
     int *words;           // [cap] number of non-empty hit words of each particle (> kMaskWords = overflow)
+    int *ovf;             // [cap + 1] ovf[0] = number of overflow particles of this step, ovf[1..] = their indices
 };
 
 struct GridBuffers {
@@ -47,8 +48,10 @@ void launch_forces(const float4 *pos_s, const float4 *vel_s, const float4 *dp, c
 void launch_density_mask(const NbBuffers &nb, const float4 *vel_s, const int *key_s, const int *cell_start, float4 *dp,
                          int *nb_count, int n, const Params &P, cudaStream_t st);
 // [i0, i1) = index range of the canonical order to process (the whole array outside slab mode)
+// pos_out != NULL: fused with the wall term + integration (new state written to pos_out/vel_out, pos_s supplies the ids)
 void launch_forces_mask(const NbBuffers &nb, const float4 *dp, const int *nb_count, const int *key_s, const int *cell_start,
-                        float4 *acc, int i0, int i1, const Params &P, cudaStream_t st);
+                        float4 *acc, int i0, int i1, const Params &P, cudaStream_t st, const float4 *pos_s = nullptr,
+                        float4 *pos_out = nullptr, float4 *vel_out = nullptr);
 // far_movers (may be NULL): slab mode counter of particles that crossed more than 2 z-layers in this step
 void launch_integrate_collide(const float4 *pos_s, const float4 *vel_s, float4 *acc, float4 *pos_out, float4 *vel_out,
                               int i0, int i1, const int *key_s, int *far_movers, const Params &P, cudaStream_t st);

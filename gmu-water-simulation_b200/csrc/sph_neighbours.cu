@@ -141,10 +141,6 @@ void launch_forces(const float4 *pos_s, const float4 *vel_s, const float4 *dp, c
 // starting at 0 (the OpenCL kernel's (1,1,0) start, resources/kernels/sph_common.cl:68, is a bug the
 // CPU path does not have).  Then x' = (x + v dt) + (a dt) dt ; v' = (x' - x)/dt with one rounding per
 // operation (src/CCPUParticleSimulator.cpp:220-221) — bit-exact given the same acceleration.
-__device__ __forceinline__ float dot_exact(float ax, float ay, float az, float bx, float by, float bz) {
-    return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
-}
-
 __global__ void __launch_bounds__(256) k_integrate_collide(const float4 *__restrict__ pos, const float4 *__restrict__ vel,
                                                            float4 *__restrict__ acc, float4 *__restrict__ pos_out,
                                                            float4 *__restrict__ vel_out, int i0, int n,
@@ -154,40 +150,8 @@ __global__ void __launch_bounds__(256) k_integrate_collide(const float4 *__restr
     if (i >= n) return;
     const float4 p = __ldg(pos + i);
     const float4 v = __ldg(vel + i);
-    float4 a = acc[i];
-    float wx = 0.f, wy = 0.f, wz = 0.f;
-#pragma unroll
-    for (int w = 0; w < 6; ++w) {
-        if (w >= P.wall_count) break;
-        const WallDev W = P.walls[w];
-        const float inx = __fmul_rn(W.nx, -1.0f), iny = __fmul_rn(W.ny, -1.0f), inz = __fmul_rn(W.nz, -1.0f);
-        const double d = __dadd_rn((double)dot_exact(__fsub_rn(W.px, p.x), __fsub_rn(W.py, p.y), __fsub_rn(W.pz, p.z), inx, iny, inz),
-                                   P.wall_skin_d);
-        if (d > 0.0) {
-            const float df = (float)d;
-            wx = __fadd_rn(wx, __fmul_rn(__fmul_rn(P.wall_k_f, inx), df));
-            wy = __fadd_rn(wy, __fmul_rn(__fmul_rn(P.wall_k_f, iny), df));
-            wz = __fadd_rn(wz, __fmul_rn(__fmul_rn(P.wall_k_f, inz), df));
-            const float s = (float)__dmul_rn(P.wall_damping_d, (double)dot_exact(v.x, v.y, v.z, inx, iny, inz));
-            wx = __fadd_rn(wx, __fmul_rn(s, inx));
-            wy = __fadd_rn(wy, __fmul_rn(s, iny));
-            wz = __fadd_rn(wz, __fmul_rn(s, inz));
-        }
-    }
-    a.x = __fadd_rn(a.x, wx);
-    a.y = __fadd_rn(a.y, wy);
-    a.z = __fadd_rn(a.z, wz);
-    const float dt = P.dt;
-    float4 np;
-    np.x = __fadd_rn(__fadd_rn(p.x, __fmul_rn(v.x, dt)), __fmul_rn(__fmul_rn(a.x, dt), dt));
-    np.y = __fadd_rn(__fadd_rn(p.y, __fmul_rn(v.y, dt)), __fmul_rn(__fmul_rn(a.y, dt), dt));
-    np.z = __fadd_rn(__fadd_rn(p.z, __fmul_rn(v.z, dt)), __fmul_rn(__fmul_rn(a.z, dt), dt));
-    np.w = p.w;
-    float4 nv;
-    nv.x = __fdiv_rn(__fsub_rn(np.x, p.x), dt);
-    nv.y = __fdiv_rn(__fsub_rn(np.y, p.y), dt);
-    nv.z = __fdiv_rn(__fsub_rn(np.z, p.z), dt);
-    nv.w = 0.0f;
+    float4 a = acc[i], np, nv;
+    walls_and_integrate(p, v, a, np, nv, P);
     if (far_movers) {
         // slab mode: the ghost exchange assumes a particle crosses at most 2 z-layers per step; count offenders
         const int old_layer = __ldg(key + i) / (P.rx * P.ry) + P.z_base;

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(128, 8) k_density_mask(const float *__restrict
                                                       const int *__restrict__ key, const int *__restrict__ cell_start,
                                                       float4 *__restrict__ dp, float4 *__restrict__ fdat,
                                                       uint2 *__restrict__ mask, int *__restrict__ nb_count,
-                                                      int *__restrict__ nb_words, int n,
+                                                      int *__restrict__ nb_words, int *__restrict__ ovf, int n,
                                                       const __grid_constant__ Params P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ __align__(16) float s_x[STAGED ? 9 : 1][STAGED ? kStageCap + 8 : 4];
@@ -237,17 +237,19 @@ __global__ void __launch_bounds__(128, 8) k_density_mask(const float *__restrict
     __stcs(fdat + 2 * (size_t)i + 1, make_float4(v.x, v.y, v.z, inv_rho));
     __stcs(nb_count + i, cnt);
     __stcs(nb_words + i, widx);  // > kMaskWords: the force pass takes the overflow path for this particle
+    if (widx > kMaskWords) ovf[1 + atomicAdd(ovf, 1)] = i;
 }
 
 void launch_density_mask(const NbBuffers &nb, const float4 *vel_s, const int *key_s, const int *cell_start, float4 *dp,
                          int *nb_count, int n, const Params &P, cudaStream_t st) {
     if (n <= 0) return;
+    cudaMemsetAsync(nb.ovf, 0, sizeof(int), st);
     if (P.tuning & 2)
         k_density_mask<true><<<(n + 127) / 128, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, vel_s, key_s, cell_start, dp, nb.fdat,
-                                                              nb.mask, nb_count, nb.words, n, P);
+                                                              nb.mask, nb_count, nb.words, nb.ovf, n, P);
     else
         k_density_mask<false><<<(n + 127) / 128, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, vel_s, key_s, cell_start, dp, nb.fdat,
-                                                               nb.mask, nb_count, nb.words, n, P);
+                                                               nb.mask, nb_count, nb.words, nb.ovf, n, P);
 }
 
 // ================================================================= forces from the bitmask
@@ -281,36 +283,78 @@ __device__ __forceinline__ float4 force_result(const ForceSum &f, const float rh
                        (f.pz * sp + f.vz * sv + P.gz * rho) / rho, 0.0f);
 }
 
-// Particles whose hit words did not fit (> kMaskWords non-empty words, extremely dense clumps) are skipped by the
-// main kernel and handled here: walk all 27 cells with the exact predicate, like the variant-0 kernel.
-__global__ void __launch_bounds__(128) k_forces_overflow(const float *__restrict__ xs, const float *__restrict__ ys,
-                                                         const float *__restrict__ zs, const float4 *__restrict__ fdat,
-                                                         const float4 *__restrict__ dp, const int *__restrict__ nb_words,
-                                                         const int *__restrict__ key, const int *__restrict__ cell_start,
-                                                         float4 *__restrict__ acc, int i0, int n,
-                                                         const __grid_constant__ Params P) {
-    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || __ldg(nb_words + i) <= kMaskWords) return;
-    float4 pi, vi;
-    ld256(fdat + 2 * (size_t)i, pi, vi);
-    ForceSum f = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for_each_row(__ldg(key + i), cell_start, P, [&](int a, int b) {
-        for (int j = a; j < b; ++j) {
-            const float r2 = r2_exact(pi.x - __ldg(xs + j), pi.y - __ldg(ys + j), pi.z - __ldg(zs + j));
-            if (P.h2 - r2 >= 0.0f && j != i) {
-                float4 pj, vj;
-                ld256(fdat + 2 * (size_t)j, pj, vj);
-                pair_term(f, pi, vi, pj, vj, false, P);
-            }
-        }
-    });
-    acc[i] = force_result(f, __ldg(&dp[i].x), P);
+// Epilogue of both force kernels.  FUSED (whole-step path): the wall term and the integration run right here -
+// the particle's position and velocity are already in registers (its own fdat record) - and the new state goes
+// to the A buffers; the separate integrate kernel and a round trip of acc through HBM disappear.  Bitwise the
+// same result as forces + k_integrate_collide.
+template <bool FUSED>
+__device__ __forceinline__ void force_epilogue(const int i, const ForceSum &f, const float4 pi, const float4 vi,
+                                               const float4 *__restrict__ dp, const float4 *__restrict__ pos_s,
+                                               float4 *__restrict__ acc, float4 *__restrict__ pos_out,
+                                               float4 *__restrict__ vel_out, const Params &P) {
+    float4 a = force_result(f, __ldg(&dp[i].x), P);
+    if (FUSED) {
+        const float4 p = make_float4(pi.x, pi.y, pi.z, __ldg(&pos_s[i].w));  // .w carries the particle id
+        const float4 v = make_float4(vi.x, vi.y, vi.z, 0.0f);
+        float4 np, nv;
+        walls_and_integrate(p, v, a, np, nv, P);
+        pos_out[i] = np;
+        vel_out[i] = nv;
+    }
+    acc[i] = a;
 }
 
+// Particles whose hit words did not fit (> kMaskWords non-empty words, extremely dense clumps) are skipped by the
+// main kernel and handled here: walk all 27 cells with the exact predicate, like the variant-0 kernel.
+template <bool FUSED>
+__global__ void __launch_bounds__(128) k_forces_overflow(const float *__restrict__ xs, const float *__restrict__ ys,
+                                                         const float *__restrict__ zs, const float4 *__restrict__ fdat,
+                                                         const float4 *__restrict__ dp, const int *__restrict__ ovf,
+                                                         const int *__restrict__ key, const int *__restrict__ cell_start,
+                                                         float4 *__restrict__ acc, const float4 *__restrict__ pos_s,
+                                                         float4 *__restrict__ pos_out, float4 *__restrict__ vel_out,
+                                                         int i0, int n, const __grid_constant__ Params P) {
+    // One WARP per overflow particle (the list the density pass recorded is normally empty or short): the lanes
+    // stride over the candidates of each row, and the partial sums are combined with a fixed-order butterfly, so
+    // the result is still a pure function of the state.
+    const int count = ovf[0];
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < count; t += warps) {
+        const int i = ovf[1 + t];
+        if (i < i0 || i >= n) continue;  // slab mode: outside the sub-range of this launch (uniform per warp)
+        float4 pi, vi;
+        ld256(fdat + 2 * (size_t)i, pi, vi);
+        ForceSum f = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for_each_row(__ldg(key + i), cell_start, P, [&](int a, int b) {
+            for (int j = a + lane; j < b; j += 32) {
+                const float r2 = r2_exact(pi.x - __ldg(xs + j), pi.y - __ldg(ys + j), pi.z - __ldg(zs + j));
+                if (P.h2 - r2 >= 0.0f && j != i) {
+                    float4 pj, vj;
+                    ld256(fdat + 2 * (size_t)j, pj, vj);
+                    pair_term(f, pi, vi, pj, vj, false, P);
+                }
+            }
+        });
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            f.px += __shfl_xor_sync(0xffffffffu, f.px, d);
+            f.py += __shfl_xor_sync(0xffffffffu, f.py, d);
+            f.pz += __shfl_xor_sync(0xffffffffu, f.pz, d);
+            f.vx += __shfl_xor_sync(0xffffffffu, f.vx, d);
+            f.vy += __shfl_xor_sync(0xffffffffu, f.vy, d);
+            f.vz += __shfl_xor_sync(0xffffffffu, f.vz, d);
+        }
+        if (lane == 0) force_epilogue<FUSED>(i, f, pi, vi, dp, pos_s, acc, pos_out, vel_out, P);
+    }
+}
+
+template <bool FUSED>
 __global__ void __launch_bounds__(128) k_forces_mask(const float4 *__restrict__ fdat, const float4 *__restrict__ dp,
                                                      const uint2 *__restrict__ mask, const int *__restrict__ nb_words,
-                                                     float4 *__restrict__ acc, int i0, int n,
-                                                     const __grid_constant__ Params P) {
+                                                     float4 *__restrict__ acc, const float4 *__restrict__ pos_s,
+                                                     float4 *__restrict__ pos_out, float4 *__restrict__ vel_out, int i0,
+                                                     int n, const __grid_constant__ Params P) {
     const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;  // particles [i0, n): slab mode runs sub-ranges
     if (i >= n) return;
     const int nw = __ldg(nb_words + i);
@@ -339,16 +383,24 @@ __global__ void __launch_bounds__(128) k_forces_mask(const float4 *__restrict__ 
         ld256(fdat + 2 * (size_t)j, pj, vj);
         pair_term(f, pi, vi, pj, vj, j == i, P);
     }
-    acc[i] = force_result(f, __ldg(&dp[i].x), P);
+    force_epilogue<FUSED>(i, f, pi, vi, dp, pos_s, acc, pos_out, vel_out, P);
 }
 
 void launch_forces_mask(const NbBuffers &nb, const float4 *dp, const int *nb_count, const int *key_s, const int *cell_start,
-                        float4 *acc, int i0, int i1, const Params &P, cudaStream_t st) {
+                        float4 *acc, int i0, int i1, const Params &P, cudaStream_t st, const float4 *pos_s, float4 *pos_out,
+                        float4 *vel_out) {
     if (i1 <= i0) return;
     (void)nb_count;
     const int grid = (i1 - i0 + 127) / 128;
-    k_forces_mask<<<grid, 128, 0, st>>>(nb.fdat, dp, nb.mask, nb.words, acc, i0, i1, P);
-    k_forces_overflow<<<grid, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, nb.fdat, dp, nb.words, key_s, cell_start, acc, i0, i1, P);
+    if (pos_out) {  // fused with walls + integration
+        k_forces_mask<true><<<grid, 128, 0, st>>>(nb.fdat, dp, nb.mask, nb.words, acc, pos_s, pos_out, vel_out, i0, i1, P);
+        k_forces_overflow<true><<<148 * 4, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, nb.fdat, dp, nb.ovf, key_s, cell_start, acc, pos_s,
+                                                      pos_out, vel_out, i0, i1, P);
+    } else {
+        k_forces_mask<false><<<grid, 128, 0, st>>>(nb.fdat, dp, nb.mask, nb.words, acc, nullptr, nullptr, nullptr, i0, i1, P);
+        k_forces_overflow<false><<<148 * 4, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, nb.fdat, dp, nb.ovf, key_s, cell_start, acc,
+                                                       nullptr, nullptr, nullptr, i0, i1, P);
+    }
 }
 
 }  // namespace sph

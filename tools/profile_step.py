@@ -28,4 +28,4 @@ for _ in range(a.steps):
     ms["density"] += ctx.density_pressure()
     ms["forces"] += ctx.forces()
     ms["integrate"] += ctx.integrate()
-print({k: round(v / a.steps, 4) for k, v in ms.items()}, "particles", sim.n)
+print({k: round(v / a.steps, 4) for k, v in ms.items()}, "particles", sim.n, "overflow particles", ctx.counter("overflow_particles"))
