@@ -22,6 +22,8 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -78,6 +80,7 @@ struct OracleSim {
     // CGrid: one vector of particle ids per cell (include/CGrid.h:24-28, src/CGrid.cpp:17-18)
     std::vector<std::vector<int32_t>> cells;
     Wall walls[6];
+    int threads = 1;  // 1 = the reference's behaviour (single-threaded); > 1 only for the labelled all-cores baseline
     // kernel coefficients, function-local statics in the reference (src/CCPUParticleSimulator.cpp:11,19,26)
     double poly6, spiky, visc, h_squared;
 
@@ -196,6 +199,12 @@ void oracle_set_state(OracleSim *s, int64_t n, const float *pos, const float *ve
 
 void oracle_set_gravity(OracleSim *s, float gx, float gy, float gz) { s->gravity = V3(gx, gy, gz); }
 
+int oracle_set_threads(OracleSim *s, int threads) {
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    s->threads = threads < 1 ? 1 : threads;
+    return s->threads;
+}
+
 int oracle_generate_particles(OracleSim *s) {
     // src/CBaseParticleSimulator.cpp:187-210
     if (s->scenario != ORACLE_FOUNTAIN) return 0;
@@ -255,6 +264,30 @@ static inline void for_neighbours(const OracleSim *s, int x, int y, int z, F &&f
     }
 }
 
+// Cell traversal of the density and force loops: x, y, z nested like the reference
+// (src/CCPUParticleSimulator.cpp:98-100).  With threads > 1 (NOT reference behaviour, labelled all-cores baseline)
+// the (x, y) columns are handed out to std::threads; every particle's sum only reads shared state and runs in the
+// same order as in the serial loop, so the results are bit-identical.
+template <typename F>
+static inline void for_cells(OracleSim *s, F &&f) {
+    const int nx = s->res[0], ny = s->res[1], nz = s->res[2];
+    if (s->threads <= 1) {
+        for (int x = 0; x < nx; x++)
+            for (int y = 0; y < ny; y++)
+                for (int z = 0; z < nz; z++) f(x, y, z);
+        return;
+    }
+    std::atomic<int> next(0);
+    auto worker = [&]() {
+        for (int c = next.fetch_add(1); c < nx * ny; c = next.fetch_add(1))
+            for (int z = 0; z < nz; z++) f(c / ny, c % ny, z);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < s->threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+}
+
 static inline void density_add(OracleSim *s, int32_t i, int32_t j) {
     // src/CCPUParticleSimulator.cpp:122-127 and Wpoly6 :9-15
     V3 distance = s->pos[i] - s->pos[j];
@@ -274,14 +307,13 @@ static inline void density_finish(OracleSim *s, int32_t i) {
 double oracle_update_density_pressure(OracleSim *s) {
     // src/CCPUParticleSimulator.cpp:93-141
     double t0 = now_ms();
-    for (int x = 0; x < s->res[0]; x++)
-        for (int y = 0; y < s->res[1]; y++)
-            for (int z = 0; z < s->res[2]; z++)
-                for (int32_t i : s->at(x, y, z)) {
-                    s->density[i] = 0.0f;
-                    for_neighbours(s, x, y, z, [&](int32_t j) { density_add(s, i, j); });
-                    density_finish(s, i);
-                }
+    for_cells(s, [&](int x, int y, int z) {
+        for (int32_t i : s->at(x, y, z)) {
+            s->density[i] = 0.0f;
+            for_neighbours(s, x, y, z, [&](int32_t j) { density_add(s, i, j); });
+            density_finish(s, i);
+        }
+    });
     return now_ms() - t0;
 }
 
@@ -329,14 +361,13 @@ static inline void force_finish(OracleSim *s, int32_t i, ForceAcc &fa) {
 double oracle_update_forces(OracleSim *s) {
     // src/CCPUParticleSimulator.cpp:143-203
     double t0 = now_ms();
-    for (int x = 0; x < s->res[0]; x++)
-        for (int y = 0; y < s->res[1]; y++)
-            for (int z = 0; z < s->res[2]; z++)
-                for (int32_t i : s->at(x, y, z)) {
-                    ForceAcc fa;
-                    for_neighbours(s, x, y, z, [&](int32_t j) { force_add(s, i, j, fa); });
-                    force_finish(s, i, fa);
-                }
+    for_cells(s, [&](int x, int y, int z) {
+        for (int32_t i : s->at(x, y, z)) {
+            ForceAcc fa;
+            for_neighbours(s, x, y, z, [&](int32_t j) { force_add(s, i, j, fa); });
+            force_finish(s, i, fa);
+        }
+    });
     return now_ms() - t0;
 }
 

@@ -41,6 +41,9 @@ void oracle_set_state(OracleSim *s, int64_t n, const float *pos, const float *ve
 /* addParticle (src/CBaseParticleSimulator.cpp:67-74) */
 void oracle_add_particle(OracleSim *s, float x, float y, float z, float vx, float vy, float vz);
 void oracle_set_gravity(OracleSim *s, float gx, float gy, float gz);
+/* NOT reference behaviour (the reference CPU path is single-threaded): run the density and force loops on `threads`
+ * std::threads (<= 0: all cores) for the labelled all-cores baseline; results stay bit-identical. Returns the count used. */
+int oracle_set_threads(OracleSim *s, int threads);
 
 /* generateParticles (src/CBaseParticleSimulator.cpp:187-210); returns #particles added */
 int oracle_generate_particles(OracleSim *s);

@@ -33,6 +33,7 @@ def _load():
         "oracle_set_state": (None, [vp, i64, vp, vp]),
         "oracle_add_particle": (None, [vp, f, f, f, f, f, f]),
         "oracle_set_gravity": (None, [vp, f, f, f]),
+        "oracle_set_threads": (i32, [vp, i32]),
         "oracle_generate_particles": (i32, [vp]),
         "oracle_update_grid": (d, [vp]),
         "oracle_update_density_pressure": (d, [vp]),
@@ -110,6 +111,10 @@ class Oracle:
 
     def set_gravity(self, g):
         lib().oracle_set_gravity(self._h, *[float(v) for v in g])
+
+    def set_threads(self, threads=0):
+        """NOT reference behaviour: worker threads for the labelled all-cores baseline (0 = all cores)."""
+        return lib().oracle_set_threads(self._h, int(threads))
 
     def generate_particles(self):
         return lib().oracle_generate_particles(self._h)
