@@ -468,11 +468,10 @@ int slab_step_overlapped(sph_context *c, int n_steps, double *ms) {
         enqueue_density(c);  // all local particles: the first ghost layer needs its density too
         CUDA_TRY(c, cudaEventSynchronize(s.ev_ranges));  // returns while the density pass is still running
         const int L0 = s.h_pinned[4], L1 = s.h_pinned[5], L2 = s.h_pinned[6], L3 = s.h_pinned[7];
-        auto forces_integrate = [&](int i0, int i1) {
-            launch_forces_mask(c->nb, c->dp, c->nb_count, c->g.key_s, c->g.cell_start, c->acc, i0, i1, c->P, c->stream);
-            launch_integrate_collide(c->pos_s, c->vel_s, c->acc, c->pos_a, c->vel_a, i0, i1, c->g.key_s, s.d_counters + 4,
-                                     c->P, c->stream);
-            c->kernel_launches += 3;
+        auto forces_integrate = [&](int i0, int i1) {  // fused forces + walls + integration on [i0, i1)
+            launch_forces_mask(c->nb, c->dp, c->nb_count, c->g.key_s, c->g.cell_start, c->acc, i0, i1, c->P, c->stream,
+                               c->pos_s, c->pos_a, c->vel_a, s.d_counters + 4);
+            c->kernel_launches += 2;
         };
         forces_integrate(L0, L1);
         forces_integrate(L2, L3);

@@ -51,7 +51,7 @@ void launch_density_mask(const NbBuffers &nb, const float4 *vel_s, const int *ke
 // pos_out != NULL: fused with the wall term + integration (new state written to pos_out/vel_out, pos_s supplies the ids)
 void launch_forces_mask(const NbBuffers &nb, const float4 *dp, const int *nb_count, const int *key_s, const int *cell_start,
                         float4 *acc, int i0, int i1, const Params &P, cudaStream_t st, const float4 *pos_s = nullptr,
-                        float4 *pos_out = nullptr, float4 *vel_out = nullptr);
+                        float4 *pos_out = nullptr, float4 *vel_out = nullptr, int *far_movers = nullptr);
 // far_movers (may be NULL): slab mode counter of particles that crossed more than 2 z-layers in this step
 void launch_integrate_collide(const float4 *pos_s, const float4 *vel_s, float4 *acc, float4 *pos_out, float4 *vel_out,
                               int i0, int i1, const int *key_s, int *far_movers, const Params &P, cudaStream_t st);

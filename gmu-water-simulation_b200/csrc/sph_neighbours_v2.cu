@@ -291,13 +291,20 @@ template <bool FUSED>
 __device__ __forceinline__ void force_epilogue(const int i, const ForceSum &f, const float4 pi, const float4 vi,
                                                const float4 *__restrict__ dp, const float4 *__restrict__ pos_s,
                                                float4 *__restrict__ acc, float4 *__restrict__ pos_out,
-                                               float4 *__restrict__ vel_out, const Params &P) {
+                                               float4 *__restrict__ vel_out, const int *__restrict__ key,
+                                               int *__restrict__ far_movers, const Params &P) {
     float4 a = force_result(f, __ldg(&dp[i].x), P);
     if (FUSED) {
         const float4 p = make_float4(pi.x, pi.y, pi.z, __ldg(&pos_s[i].w));  // .w carries the particle id
         const float4 v = make_float4(vi.x, vi.y, vi.z, 0.0f);
         float4 np, nv;
         walls_and_integrate(p, v, a, np, nv, P);
+        if (far_movers) {
+            // slab mode: the ghost exchange assumes a particle crosses at most 2 z-layers per step; count offenders
+            const int old_layer = __ldg(key + i) / (P.rx * P.ry) + P.z_base;
+            const int new_layer = cell_coord(np.z, P.hbz, P.h_d, P.rz_global);
+            if (abs(new_layer - old_layer) > 2) atomicAdd(far_movers, 1);
+        }
         pos_out[i] = np;
         vel_out[i] = nv;
     }
@@ -313,7 +320,8 @@ __global__ void __launch_bounds__(128) k_forces_overflow(const float *__restrict
                                                          const int *__restrict__ key, const int *__restrict__ cell_start,
                                                          float4 *__restrict__ acc, const float4 *__restrict__ pos_s,
                                                          float4 *__restrict__ pos_out, float4 *__restrict__ vel_out,
-                                                         int i0, int n, const __grid_constant__ Params P) {
+                                                         int *__restrict__ far_movers, int i0, int n,
+                                                         const __grid_constant__ Params P) {
     // One WARP per overflow particle (the list the density pass recorded is normally empty or short): the lanes
     // stride over the candidates of each row, and the partial sums are combined with a fixed-order butterfly, so
     // the result is still a pure function of the state.
@@ -345,7 +353,7 @@ __global__ void __launch_bounds__(128) k_forces_overflow(const float *__restrict
             f.vy += __shfl_xor_sync(0xffffffffu, f.vy, d);
             f.vz += __shfl_xor_sync(0xffffffffu, f.vz, d);
         }
-        if (lane == 0) force_epilogue<FUSED>(i, f, pi, vi, dp, pos_s, acc, pos_out, vel_out, P);
+        if (lane == 0) force_epilogue<FUSED>(i, f, pi, vi, dp, pos_s, acc, pos_out, vel_out, key, far_movers, P);
     }
 }
 
@@ -353,7 +361,8 @@ template <bool FUSED>
 __global__ void __launch_bounds__(128) k_forces_mask(const float4 *__restrict__ fdat, const float4 *__restrict__ dp,
                                                      const uint2 *__restrict__ mask, const int *__restrict__ nb_words,
                                                      float4 *__restrict__ acc, const float4 *__restrict__ pos_s,
-                                                     float4 *__restrict__ pos_out, float4 *__restrict__ vel_out, int i0,
+                                                     float4 *__restrict__ pos_out, float4 *__restrict__ vel_out,
+                                                     const int *__restrict__ key, int *__restrict__ far_movers, int i0,
                                                      int n, const __grid_constant__ Params P) {
     const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;  // particles [i0, n): slab mode runs sub-ranges
     if (i >= n) return;
@@ -383,23 +392,25 @@ __global__ void __launch_bounds__(128) k_forces_mask(const float4 *__restrict__ 
         ld256(fdat + 2 * (size_t)j, pj, vj);
         pair_term(f, pi, vi, pj, vj, j == i, P);
     }
-    force_epilogue<FUSED>(i, f, pi, vi, dp, pos_s, acc, pos_out, vel_out, P);
+    force_epilogue<FUSED>(i, f, pi, vi, dp, pos_s, acc, pos_out, vel_out, key, far_movers, P);
 }
 
 void launch_forces_mask(const NbBuffers &nb, const float4 *dp, const int *nb_count, const int *key_s, const int *cell_start,
                         float4 *acc, int i0, int i1, const Params &P, cudaStream_t st, const float4 *pos_s, float4 *pos_out,
-                        float4 *vel_out) {
+                        float4 *vel_out, int *far_movers) {
     if (i1 <= i0) return;
     (void)nb_count;
     const int grid = (i1 - i0 + 127) / 128;
     if (pos_out) {  // fused with walls + integration
-        k_forces_mask<true><<<grid, 128, 0, st>>>(nb.fdat, dp, nb.mask, nb.words, acc, pos_s, pos_out, vel_out, i0, i1, P);
-        k_forces_overflow<true><<<148 * 4, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, nb.fdat, dp, nb.ovf, key_s, cell_start, acc, pos_s,
-                                                      pos_out, vel_out, i0, i1, P);
+        k_forces_mask<true><<<grid, 128, 0, st>>>(nb.fdat, dp, nb.mask, nb.words, acc, pos_s, pos_out, vel_out, key_s,
+                                                  far_movers, i0, i1, P);
+        k_forces_overflow<true><<<148 * 4, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, nb.fdat, dp, nb.ovf, key_s, cell_start, acc,
+                                                         pos_s, pos_out, vel_out, far_movers, i0, i1, P);
     } else {
-        k_forces_mask<false><<<grid, 128, 0, st>>>(nb.fdat, dp, nb.mask, nb.words, acc, nullptr, nullptr, nullptr, i0, i1, P);
+        k_forces_mask<false><<<grid, 128, 0, st>>>(nb.fdat, dp, nb.mask, nb.words, acc, nullptr, nullptr, nullptr, nullptr,
+                                                   nullptr, i0, i1, P);
         k_forces_overflow<false><<<148 * 4, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, nb.fdat, dp, nb.ovf, key_s, cell_start, acc,
-                                                       nullptr, nullptr, nullptr, i0, i1, P);
+                                                          nullptr, nullptr, nullptr, nullptr, i0, i1, P);
     }
 }
 
