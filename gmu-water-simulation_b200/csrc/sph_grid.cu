@@ -177,9 +177,13 @@ __global__ void __launch_bounds__(256) k_rank_scatter(const float4 *__restrict__
     vel_s[dst] = __ldg(vel_a + src);
     key_s[dst] = k;
     if (xs) {
-        xs[dst] = p.x;
-        ys[dst] = p.y;
-        zs[dst] = p.z;
+        // A particle with a non-finite coordinate can be nobody's neighbour in the reference (every comparison
+        // with NaN is false).  The bitmask pass takes the hit from the sign bit of h2 - r2, so such a particle is
+        // given the far-away sentinel in the candidate arrays instead; pos_s keeps its real value.
+        const bool ok = isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+        xs[dst] = ok ? p.x : 1.0e18f;
+        ys[dst] = ok ? p.y : 1.0e18f;
+        zs[dst] = ok ? p.z : 1.0e18f;
     }
 }
 

@@ -440,3 +440,27 @@ def test_headless_cpp_bench_runs(gws):
     assert out.returncode == 0, out.stderr[-500:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["particles"] == 210 and line["phase_ms"]["density"] > 0 and line["phase_ms"]["collisions"] == 0
+
+
+@pytest.mark.parametrize("variant", [1, 0])
+def test_non_finite_particle_stays_confined(gws, variant):
+    """A particle with a NaN coordinate is nobody's neighbour in the reference (comparisons with NaN are false) and
+    lands in cell 0 after clamping; the rest of the scene must be unaffected - same sets, same densities."""
+    o = state_after(0.4, 6)
+    pos, vel = o.pos.copy(), o.vel.copy()
+    bad = 777
+    pos[bad] = [np.nan, 0.01, 0.02]
+    o = Oracle(0.4).set_state(pos, vel)
+    ctx = make_ctx(gws, 0.4, pos, vel, variant=variant)
+    o.update_grid(); ctx.update_grid()
+    assert np.array_equal(ctx.keys(), o.keys())
+    o.update_density_pressure(); ctx.density_pressure()
+    oc, _ = o.neighbours(lists=False)
+    gc, _ = ctx.neighbours(lists=False)
+    others = np.arange(o.n) != bad
+    assert np.array_equal(gc[others], oc[others]) and oc[bad] == 0
+    rho, prs, _ = ctx.density_pressure_accel()
+    assert np.all(np.abs(rho[others] - o.density[others]) <= RTOL * o.density[others])
+    o.update_forces(); ctx.forces(); ctx.integrate()
+    rec = ctx.download()
+    assert np.isfinite(rec["position"][others, :3]).all() and np.isfinite(rec["acceleration"][others, :3]).all()
