@@ -155,6 +155,7 @@ def host_lib():
             "gmu_sim_step_many": (i32, [vp, i32, C.POINTER(dbl)]),
             "gmu_sim_emit": (i32, [vp, i32]),
             "gmu_sim_set_mirror_mode": (i32, [vp, i32]),
+            "gmu_sim_set_mirror_stride": (i32, [vp, i32]),
             "gmu_sim_sync_host": (i32, [vp]),
             "gmu_sim_set_gravity": (i32, [vp, f, f, f]),
             "gmu_sim_key": (i32, [vp, i32]),
@@ -476,6 +477,9 @@ class Simulator:
 
     def set_mirror_mode(self, mode):
         self._ck(self.lib.gmu_sim_set_mirror_mode(self._h, int(mode)))
+
+    def set_mirror_stride(self, stride):
+        self._ck(self.lib.gmu_sim_set_mirror_stride(self._h, int(stride)))
 
     def sync_host(self):
         self._ck(self.lib.gmu_sim_sync_host(self._h))

@@ -99,7 +99,8 @@ void CCUDAParticleSimulator::step() {
                                                m_deviceCount), "step upload");
         }
         CBaseParticleSimulator::step();
-        if (m_mirrorMode != Resident) syncHostMirror();
+        if (m_mirrorMode == RoundTrip || (m_mirrorMode == Download && (getTotalIteration() + 1) % (unsigned long)m_mirrorStride == 0))
+            syncHostMirror();
     } catch (CUDAException &exc) {
         emitErrorOccured(exc.what());
         stop();

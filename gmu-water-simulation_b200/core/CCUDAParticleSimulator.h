@@ -36,6 +36,9 @@ public:
     void stepMany(int steps, double *deviceMs = nullptr);  // fused steps on the device (dam break: one CUDA graph)
     void syncHostMirror();                                 // device -> m_clParticles (indexed by id)
     void setMirrorMode(MirrorMode m) { m_mirrorMode = m; }
+    // viewer bridge: in Download mode refresh the host mirror only every `stride`-th step (a 60 Hz viewer does not
+    // need 1500 read-backs per second); 1 = every step like the reference's OpenCL path
+    void setMirrorStride(int stride) { m_mirrorStride = stride < 1 ? 1 : stride; }
     void setBruteForce(bool on) { m_brute = on; }          // CGPUBruteParticleSimulator semantics (all pairs)
     // Multi-GPU extension: make this instance rank `rank` of `world` z-slabs (call before setupScene).  ncclId is
     // the 128-byte id from sph_comm_unique_id(), identical on all ranks.  In slab mode the host mirror holds this
@@ -62,6 +65,7 @@ private:
     int m_device;
     std::unique_ptr<CUDAWrapper> m_cuda;
     MirrorMode m_mirrorMode = Resident;
+    int m_mirrorStride = 1;
     bool m_brute = false;
     cl_uint m_deviceCount = 0;  // particles already on the device
 };

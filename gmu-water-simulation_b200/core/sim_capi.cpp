@@ -122,6 +122,13 @@ int gmu_sim_set_mirror_mode(gmu_sim *s, int mode) {
     });
 }
 
+int gmu_sim_set_mirror_stride(gmu_sim *s, int stride) {
+    return guarded([&] {
+        if (!H(s)->cuda) throw std::runtime_error("gmu_sim_set_mirror_stride: not a CUDA simulator");
+        H(s)->cuda->setMirrorStride(stride);
+    });
+}
+
 int gmu_sim_sync_host(gmu_sim *s) {
     return guarded([&] {
         if (!H(s)->cuda) throw std::runtime_error("gmu_sim_sync_host: not a CUDA simulator");

@@ -245,10 +245,22 @@ def test_simulator_phase_path_and_mirror_modes(gws):
     assert np.abs(hp["position"][:, :3] - o.pos).max() <= 1e-4 * 0.0457
     ev = sim.events()
     assert ev.shape == (3, 7) and np.all(ev[:, 2:5] > 0) and np.all(ev[:, 5] == 0)
+    # decimated viewer refresh: download mode with stride 4 only touches the mirror on every 4th step
+    sim.set_mirror_mode(1)
+    sim.set_mirror_stride(4)
+    before = sim.host_particles()["position"].copy()
+    sim.step(1)           # iteration 4 -> refresh
+    o.step(1)
+    assert np.abs(sim.host_particles()["position"][:, :3] - o.pos).max() <= 1e-4 * 0.0457
+    before = sim.host_particles()["position"].copy()
+    sim.step(2)           # iterations 5, 6 -> mirror untouched
+    o.step(2)
+    assert np.array_equal(before, sim.host_particles()["position"])
+    sim.set_mirror_stride(1)
     # resident fused path continues from the same state
     sim.set_mirror_mode(0)
-    sim.step_many(7)
-    o.step(7)
+    sim.step_many(4)
+    o.step(4)
     sim.sync_host()
     assert np.abs(sim.host_particles()["position"][:, :3] - o.pos).max() <= 2e-4 * 0.0457
     assert sim.iteration == 10
