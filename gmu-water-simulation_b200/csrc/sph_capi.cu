@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -119,6 +120,8 @@ Params make_params(const sph_config &c) {
     P.ry = c.grid_res[1];
     P.rz = c.grid_res[2];
     P.n_cells = P.rx * P.ry * P.rz;
+    P.xb = 1;
+    P.h_win = (double)c.h * (1.0 + 1e-6);
     P.rz_global = P.rz;
     P.z_base = 0;
     // src/CCPUParticleSimulator.cpp:46-48: m_boxSize.x() / 2.0 and CParticle::h widen to double
@@ -411,7 +414,7 @@ int slab_exchange(sph_context *c) {
 // Read back the first particle index of up to 4 local z-layers (cell_start at layer boundaries).
 int slab_layer_starts(sph_context *c, const int layers[4], int out[4]) {
     Slab &s = *c->slab;
-    const size_t rxy = (size_t)c->P.rx * c->P.ry;
+    const size_t rxy = (size_t)c->P.rx * c->P.xb * c->P.ry;  // sort-key entries per z-layer
     for (int k = 0; k < 4; ++k)
         CUDA_TRY(c, cudaMemcpyAsync(s.h_pinned + 4 + k, c->g.cell_start + (size_t)layers[k] * rxy, sizeof(int),
                                     cudaMemcpyDeviceToHost, c->stream));
@@ -601,9 +604,18 @@ int sph_create(const sph_config *cfg, sph_context **out) {
     c->cfg = *cfg;
     c->device = cfg->device;
     c->P = make_params(*cfg);
+    // x bins per cell of the sort key: 4 by default (the density pass then scans 9 of 12 bins per row); 1 for grids
+    // too narrow for the bitmask passes; SPH_XBINS overrides for experiments (1, 2, 4 or 8)
+    int xb = c->P.rx >= 4 ? 4 : 1;
+    if (const char *e = std::getenv("SPH_XBINS")) {
+        const int v = std::atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) xb = v;
+    }
+    while (xb > 1 && (double)c->P.n_cells * xb >= 2.0e9) xb >>= 1;
+    c->P.xb = xb;
     c->cap = cfg->max_particles;
     const size_t cap = c->cap;
-    const size_t items = (size_t)c->P.n_cells + 1;
+    const size_t items = (size_t)c->P.n_cells * (size_t)xb + 1;
     c->g.n_scan_items = (int)items;
     c->g.n_tiles = (int)((items + kScanTile - 1) / kScanTile);
     c->cells_padded = (size_t)c->g.n_tiles * kScanTile;
@@ -896,7 +908,7 @@ int sph_download_keys(sph_context *c, int32_t *keys) {
     REQUIRE(c, c->grid_valid, SPH_ERR_STATE, "sph_download_keys: grid not built");
     REQUIRE(c, !c->slab, SPH_ERR_STATE, "sph_download_keys: indexed by global id - not available in slab mode (use sph_download_owned)");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    launch_scatter_by_id_i32(c->pos_s, c->g.key_s, c->d_tmp_i32, (int)c->n, c->stream);
+    launch_scatter_cell_ids(c->pos_s, c->g.key_s, c->d_tmp_i32, (int)c->n, c->P, c->stream);
     c->kernel_launches += 1;
     CUDA_TRY(c, cudaMemcpyAsync(keys, c->d_tmp_i32, (size_t)c->n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -908,7 +920,9 @@ int sph_download_permutation(sph_context *c, uint32_t *sorted_ids) {
     REQUIRE(c, c->grid_valid, SPH_ERR_STATE, "sph_download_permutation: grid not built");
     REQUIRE(c, !c->slab, SPH_ERR_STATE, "sph_download_permutation: indexed by global id - not available in slab mode (use sph_download_owned)");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    launch_extract_ids(c->pos_s, reinterpret_cast<unsigned *>(c->d_tmp_i32), (int)c->n, c->stream);
+    // the device order is (cell, x bin, id); the tap reports the order stable by (cell id, particle id)
+    launch_cell_id_permutation(c->pos_s, c->g.key_s, c->g.cell_start, reinterpret_cast<unsigned *>(c->d_tmp_i32), (int)c->n,
+                               c->P, c->stream);
     c->kernel_launches += 1;
     CUDA_TRY(c, cudaMemcpyAsync(sorted_ids, c->d_tmp_i32, (size_t)c->n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -919,10 +933,16 @@ int sph_download_cell_start(sph_context *c, int32_t *cell_start) {
     REQUIRE(c, c && cell_start, SPH_ERR_ARGUMENT, "sph_download_cell_start: NULL argument");
     REQUIRE(c, c->grid_valid, SPH_ERR_STATE, "sph_download_cell_start: grid not built");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    CUDA_TRY(c, cudaMemcpyAsync(cell_start, c->g.cell_start, ((size_t)c->P.n_cells + 1) * sizeof(int),
-                                cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    return SPH_OK;
+    int *d_coarse = nullptr;  // one entry per reference cell out of the finer sort-key scan
+    CUDA_TRY(c, dalloc(&d_coarse, (size_t)c->P.n_cells + 1));
+    launch_coarse_cell_start(c->g.cell_start, d_coarse, c->P.n_cells, c->P.xb, c->stream);
+    c->kernel_launches += 1;
+    cudaError_t e = cudaMemcpyAsync(cell_start, d_coarse, ((size_t)c->P.n_cells + 1) * sizeof(int), cudaMemcpyDeviceToHost,
+                                    c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_coarse);
+    CUDA_TRY(c, e);
+    return check_launch(c, "download_cell_start");
 }
 
 int sph_download_density_pressure_accel(sph_context *c, float *density, float *pressure, float *accel3) {

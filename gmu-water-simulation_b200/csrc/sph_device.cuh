@@ -21,6 +21,8 @@ struct WallDev {
 struct Params {
     int rx, ry, rz;       // grid resolution (x fastest, z slowest: include/CGrid.h:27)
     int n_cells;          // rx*ry*rz
+    int xb;               // x bins per cell of the sort key (power of two; 1 = sort by the reference cell id only)
+    double h_win;         // h (1 + 1e-6): half-width of the candidate x-window
     int rz_global;        // z resolution of the whole tank (== rz on a single device)
     int z_base;           // slab mode: global index of local z-layer 0 (0 on a single device)
     double hbx, hby, hbz; // double(box)/2.0           (src/CCPUParticleSimulator.cpp:46-48)
@@ -53,62 +55,102 @@ __device__ __forceinline__ int cell_coord(float x, double half_box, double h_d, 
     return min(max(c, 0), res - 1);
 }
 
+// ---- sort keys ---------------------------------------------------------------------------------------
+// The device sorts by a FINE key: every reference cell is split into P.xb (1, 2, 4 or 8) bins along x,
+//   fine key = x_bin + cy * (rx*xb) + cz * (rx*xb) * ry,      x_bin = clamp(floor(q_x * xb), 0, rx*xb - 1),
+// with q_x = (double(x) + b/2)/h exactly as the reference computes it.  q_x * xb is exact for a power of two, so
+// x_bin / xb == clamp(floor(q_x)) is the reference's cell coordinate bit for bit and the reference cell id
+// (include/CGrid.h:27) is recovered with coarse_key().  The order (cell, x_bin, id) refines the cell order: a
+// reference cell is still one contiguous particle range, and inside a row the particles are roughly sorted by x, so
+// the density pass can scan an x-WINDOW of about (2 xb + 1)/(3 xb) of the row instead of all three cells.
+__device__ __forceinline__ int x_bin_unclamped(double x, const Params &P) {
+    return __double2int_rd(__dmul_rn(__ddiv_rn(__dadd_rn(x, P.hbx), P.h_d), (double)P.xb));
+}
+
 __device__ __forceinline__ int cell_key(float4 p, const Params &P) {
-    int cx = cell_coord(p.x, P.hbx, P.h_d, P.rx);
-    int cy = cell_coord(p.y, P.hby, P.h_d, P.ry);
+    const int rxb = P.rx * P.xb;
+    const int gx = min(max(x_bin_unclamped((double)p.x, P), 0), rxb - 1);
+    const int cy = cell_coord(p.y, P.hby, P.h_d, P.ry);
     // slab mode: the global layer (clamped like the reference clamps it) is shifted into the local grid
     int cz = cell_coord(p.z, P.hbz, P.h_d, P.rz_global) - P.z_base;
     cz = min(max(cz, 0), P.rz - 1);
-    return cx + cy * P.rx + cz * P.rx * P.ry;
+    return gx + cy * rxb + cz * rxb * P.ry;
 }
 
-// Same enumeration, but the callback also gets the row slot (dz+1)*3 + (dy+1) in 0..8.
+struct CellCoords {
+    int gx, cx, cy, cz;  // x bin, reference cell coordinates (cz local in slab mode)
+};
+__device__ __forceinline__ CellCoords decode_key(int key, const Params &P) {
+    const int rxb = P.rx * P.xb, plane = rxb * P.ry;
+    CellCoords c;
+    c.cz = key / plane;
+    const int rem = key - c.cz * plane;
+    c.cy = rem / rxb;
+    c.gx = rem - c.cy * rxb;
+    c.cx = c.gx / P.xb;
+    return c;
+}
+// reference cell id x + y*ResX + z*ResX*ResY (z local in slab mode)
+__device__ __forceinline__ int coarse_key(int key, const Params &P) {
+    const CellCoords c = decode_key(key, P);
+    return c.cx + c.cy * P.rx + c.cz * P.rx * P.ry;
+}
+
+// Up to 9 contiguous candidate ranges: the reference's 27 cells, x-1..x+1 merged because x is the fastest axis.
+// f(slot, a, b) gets the row slot (dz+1)*3 + (dy+1) and the sorted-particle index range [a, b), z-major.
 template <typename F>
 __device__ __forceinline__ void for_each_row_slot(int key, const int *__restrict__ cell_start, const Params &P, F &&f) {
-    const int rxy = P.rx * P.ry;
-    const int cz = key / rxy;
-    const int rem = key - cz * rxy;
-    const int cy = rem / P.rx;
-    const int cx = rem - cy * P.rx;
-    const int xl = max(cx - 1, 0), xr = min(cx + 1, P.rx - 1);
+    const CellCoords c = decode_key(key, P);
+    const int rxb = P.rx * P.xb, plane = rxb * P.ry;
+    const int xl = max(c.cx - 1, 0), xr = min(c.cx + 1, P.rx - 1);
 #pragma unroll 1
     for (int dz = -1; dz <= 1; ++dz) {
-        const int z = cz + dz;
+        const int z = c.cz + dz;
         if (z < 0 || z >= P.rz) continue;
 #pragma unroll 1
         for (int dy = -1; dy <= 1; ++dy) {
-            const int y = cy + dy;
+            const int y = c.cy + dy;
             if (y < 0 || y >= P.ry) continue;
-            const int c0 = xl + y * P.rx + z * rxy;
-            const int a = __ldg(cell_start + c0);
-            const int b = __ldg(cell_start + c0 + (xr - xl) + 1);
+            const int row = y * rxb + z * plane;
+            const int a = __ldg(cell_start + row + xl * P.xb);
+            const int b = __ldg(cell_start + row + (xr + 1) * P.xb);
             f((dz + 1) * 3 + (dy + 1), a, b);
         }
     }
 }
 
-// Up to 9 contiguous candidate ranges (x-1..x+1 merged because x is the fastest cell axis).
-// f(a, b) is called with the sorted-particle index range [a, b) of each (dy, dz) row, z-major.
 template <typename F>
 __device__ __forceinline__ void for_each_row(int key, const int *__restrict__ cell_start, const Params &P, F &&f) {
-    const int rxy = P.rx * P.ry;
-    const int cz = key / rxy;
-    const int rem = key - cz * rxy;
-    const int cy = rem / P.rx;
-    const int cx = rem - cy * P.rx;
-    const int xl = max(cx - 1, 0), xr = min(cx + 1, P.rx - 1);
+    for_each_row_slot(key, cell_start, P, [&](int, int a, int b) { f(a, b); });
+}
+
+// The same rows clipped to the x-window a particle at x = px can have neighbours in: bins
+// [bin(px - h'), bin(px + h')] with h' = h (1 + 1e-6), intersected with the reference's three cells.  A candidate j
+// that passes the fp32 predicate has |x_i - x_j| <= h (1 + 2^-22) in exact arithmetic and q_x is evaluated by the
+// same monotone fp64 expression for both, so j's bin always lies inside the window: the neighbour sets do not
+// depend on xb.
+template <typename F>
+__device__ __forceinline__ void for_each_window_slot(float px, int key, const int *__restrict__ cell_start,
+                                                     const Params &P, F &&f) {
+    const CellCoords c = decode_key(key, P);
+    const int rxb = P.rx * P.xb, plane = rxb * P.ry;
+    const int xl = max(c.cx - 1, 0), xr = min(c.cx + 1, P.rx - 1);
+    const int bl = max(x_bin_unclamped(__dsub_rn((double)px, P.h_win), P), xl * P.xb);
+    const int bh = min(x_bin_unclamped(__dadd_rn((double)px, P.h_win), P), (xr + 1) * P.xb - 1);
+    // a clamped (out-of-box) particle sits in an edge bin whatever its coordinate says: keep its own bin inside
+    const int lo = min(bl, c.gx), hi = max(bh, c.gx);
 #pragma unroll 1
     for (int dz = -1; dz <= 1; ++dz) {
-        const int z = cz + dz;
+        const int z = c.cz + dz;
         if (z < 0 || z >= P.rz) continue;
 #pragma unroll 1
         for (int dy = -1; dy <= 1; ++dy) {
-            const int y = cy + dy;
+            const int y = c.cy + dy;
             if (y < 0 || y >= P.ry) continue;
-            const int c0 = xl + y * P.rx + z * rxy;
-            const int a = __ldg(cell_start + c0);
-            const int b = __ldg(cell_start + c0 + (xr - xl) + 1);
-            f(a, b);
+            const int row = y * rxb + z * plane;
+            const int a = __ldg(cell_start + row + lo);
+            const int b = __ldg(cell_start + row + hi + 1);
+            f((dz + 1) * 3 + (dy + 1), a, b);
         }
     }
 }

@@ -25,11 +25,11 @@ struct GridBuffers {
     int *off_a;                       // [cap]   arrival offset inside the cell (atomic)
     int *bucket_src;                  // [cap]   input index per bucket slot
     int *bucket_id;                   // [cap]   particle id per bucket slot
-    int *key_s;                       // [cap]   cell id in canonical order
+    int *key_s;                       // [cap]   sort key (reference cell id refined by the x bin) in canonical order
     int *count;                       // [cells_padded] per-cell histogram (zeroed by the scan)
     int *cell_start;                  // [cells_padded] exclusive scan; [n_cells] = n
     unsigned long long *scan_status;  // [tiles + 1]: tile look-back words, last = tile ticket
-    int n_scan_items;                 // n_cells + 1
+    int n_scan_items;                 // n_cells * xb + 1
     int n_tiles;
 };
 
@@ -78,6 +78,10 @@ void launch_slab_pack(const float4 *pos, const float4 *vel, int n, int z_lo_belo
                       float4 *down_vel, float4 *up_pos, float4 *up_vel, int *counters, int cap_face, const Params &P,
                       cudaStream_t st);
 void launch_scatter_by_id_i32(const float4 *pos, const int *src, int *dst_by_id, int n, cudaStream_t st);
+void launch_scatter_cell_ids(const float4 *pos, const int *key, int *dst_by_id, int n, const Params &P, cudaStream_t st);
+void launch_coarse_cell_start(const int *cell_start, int *out, int n_cells, int xb, cudaStream_t st);
+void launch_cell_id_permutation(const float4 *pos, const int *key, const int *cell_start, unsigned *out, int n,
+                                const Params &P, cudaStream_t st);
 void launch_scatter_dpa_by_id(const float4 *pos, const float4 *dp, const float4 *acc, float *rho, float *p, float *acc3,
                               int n, cudaStream_t st);
 void launch_extract_ids(const float4 *pos, unsigned *ids, int n, cudaStream_t st);

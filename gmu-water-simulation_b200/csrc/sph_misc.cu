@@ -40,10 +40,10 @@ __global__ void __launch_bounds__(256) k_soa_to_aos(const float4 *__restrict__ p
     const float4 v = __ldg(vel + i);
     const float4 a = acc ? __ldg(acc + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 d = dp ? __ldg(dp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const int k = key ? __ldg(key + i) : 0;
-    const int rxy = P.rx * P.ry;
-    const int cz = k / rxy, cy = (k - cz * rxy) / P.rx, cx = k - cz * rxy - cy * P.rx;
-    const int cz_global = cz + P.z_base, k_global = k + P.z_base * rxy;  // slab mode reports global cells
+    const CellCoords cc = decode_key(key ? __ldg(key + i) : 0, P);  // the sort key is finer than the reference cell id
+    const int cx = cc.cx, cy = cc.cy, cz = cc.cz;
+    const int cz_global = cz + P.z_base;                            // slab mode reports global cells
+    const int k_global = cx + cy * P.rx + cz_global * P.rx * P.ry;
     float4 *rec = reinterpret_cast<float4 *>(out + slot);
     rec[0] = make_float4(p.x, p.y, p.z, 0.0f);
     rec[1] = make_float4(v.x, v.y, v.z, 0.0f);
@@ -68,6 +68,46 @@ __global__ void __launch_bounds__(256) k_scatter_by_id_i32(const float4 *__restr
 void launch_scatter_by_id_i32(const float4 *pos, const int *src, int *dst_by_id, int n, cudaStream_t st) {
     if (n <= 0) return;
     k_scatter_by_id_i32<<<(n + 255) / 256, 256, 0, st>>>(pos, src, dst_by_id, n);
+}
+
+// taps that speak the reference's cell ids: keys by id, cell_start per reference cell, (cell, id) permutation
+__global__ void __launch_bounds__(256) k_scatter_cell_ids(const float4 *__restrict__ pos, const int *__restrict__ key,
+                                                          int *__restrict__ dst, int n, const __grid_constant__ Params P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dst[__float_as_int(__ldg(&pos[i].w))] = coarse_key(__ldg(key + i), P);
+}
+void launch_scatter_cell_ids(const float4 *pos, const int *key, int *dst_by_id, int n, const Params &P, cudaStream_t st) {
+    if (n <= 0) return;
+    k_scatter_cell_ids<<<(n + 255) / 256, 256, 0, st>>>(pos, key, dst_by_id, n, P);
+}
+
+__global__ void __launch_bounds__(256) k_coarse_cell_start(const int *__restrict__ cell_start, int *__restrict__ out,
+                                                           int n_cells, int xb) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c <= n_cells) out[c] = __ldg(cell_start + (size_t)c * xb);
+}
+void launch_coarse_cell_start(const int *cell_start, int *out, int n_cells, int xb, cudaStream_t st) {
+    k_coarse_cell_start<<<(n_cells + 1 + 255) / 256, 256, 0, st>>>(cell_start, out, n_cells, xb);
+}
+
+// ids in the order stable by (reference cell id, particle id): rank inside the reference cell by id
+__global__ void __launch_bounds__(256) k_cell_id_permutation(const float4 *__restrict__ pos, const int *__restrict__ key,
+                                                             const int *__restrict__ cell_start, unsigned *__restrict__ out,
+                                                             int n, const __grid_constant__ Params P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = coarse_key(__ldg(key + i), P);
+    const int a = __ldg(cell_start + (size_t)c * P.xb), b = __ldg(cell_start + (size_t)(c + 1) * P.xb);
+    const int my_id = __float_as_int(__ldg(&pos[i].w));
+    int rank = 0;
+    for (int t = a; t < b; ++t) rank += (__float_as_int(__ldg(&pos[t].w)) < my_id);
+    out[a + rank] = (unsigned)my_id;
+}
+void launch_cell_id_permutation(const float4 *pos, const int *key, const int *cell_start, unsigned *out, int n,
+                                const Params &P, cudaStream_t st) {
+    if (n <= 0) return;
+    k_cell_id_permutation<<<(n + 255) / 256, 256, 0, st>>>(pos, key, cell_start, out, n, P);
 }
 
 __global__ void __launch_bounds__(256) k_scatter_dpa(const float4 *__restrict__ pos, const float4 *__restrict__ dp,

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) k_integrate_collide(const float4 *__restr
     walls_and_integrate(p, v, a, np, nv, P);
     if (far_movers) {
         // slab mode: the ghost exchange assumes a particle crosses at most 2 z-layers per step; count offenders
-        const int old_layer = __ldg(key + i) / (P.rx * P.ry) + P.z_base;
+        const int old_layer = __ldg(key + i) / (P.rx * P.xb * P.ry) + P.z_base;
         const int new_layer = cell_coord(np.z, P.hbz, P.h_d, P.rz_global);
         if (abs(new_layer - old_layer) > 2) atomicAdd(far_movers, 1);
     }

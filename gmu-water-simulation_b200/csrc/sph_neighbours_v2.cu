@@ -130,8 +130,10 @@ __global__ void __launch_bounds__(128, 8) k_density_mask(const float *__restrict
         if (threadIdx.x < 9) {
             const int slot = threadIdx.x;
             const int p0 = blockIdx.x * blockDim.x, p1 = min(p0 + (int)blockDim.x, n) - 1;
-            const int off = (slot % 3 - 1) * P.rx + (slot / 3 - 1) * P.rx * P.ry;
-            const int lo = max(__ldg(key + p0) + off - 1, 0), hi = min(__ldg(key + p1) + off + 1, P.n_cells - 1);
+            const int rxb = P.rx * P.xb, n_bins = P.n_cells * P.xb;
+            const int off = (slot % 3 - 1) * rxb + (slot / 3 - 1) * rxb * P.ry;
+            // every particle's window reaches at most xb + 1 bins to either side of its own bin
+            const int lo = max(__ldg(key + p0) + off - (P.xb + 1), 0), hi = min(__ldg(key + p1) + off + P.xb + 1, n_bins - 1);
             int base = 0, cnt = 0;
             if (lo <= hi) {
                 base = __ldg(cell_start + lo) & ~3;
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(128, 8) k_density_mask(const float *__restrict
     u64 sum_a = 0ull, sum_b = 0ull;  // two packed accumulators (+0.0f, +0.0f)
     float stray_sum = 0.0f;
     int cnt = 0, widx = 0;
-    for_each_row_slot(__ldg(key + i), cell_start, P, [&](const int slot, const int a, const int b) {
+    for_each_window_slot(px, __ldg(key + i), cell_start, P, [&](const int slot, const int a, const int b) {
         int j = a & ~3;
         const bool staged = STAGED && s_cnt[slot] > 0;
         const int sbase = STAGED ? s_base[slot] : 0;
@@ -301,7 +303,7 @@ __device__ __forceinline__ void force_epilogue(const int i, const ForceSum &f, c
         walls_and_integrate(p, v, a, np, nv, P);
         if (far_movers) {
             // slab mode: the ghost exchange assumes a particle crosses at most 2 z-layers per step; count offenders
-            const int old_layer = __ldg(key + i) / (P.rx * P.ry) + P.z_base;
+            const int old_layer = __ldg(key + i) / (P.rx * P.xb * P.ry) + P.z_base;
             const int new_layer = cell_coord(np.z, P.hbz, P.h_d, P.rz_global);
             if (abs(new_layer - old_layer) > 2) atomicAdd(far_movers, 1);
         }
