@@ -5,9 +5,9 @@
 
 #include <cstdio>
 #include <cstring>
-#include <fstream>
 #include <string>
 
+#include "ExportLogs.h"
 #include "SimulatorFactory.h"
 
 namespace {
@@ -184,30 +184,7 @@ uint64_t gmu_sim_get_events(gmu_sim *s, double *out, uint64_t max_events) {
 }
 
 int gmu_sim_export_logs(gmu_sim *s, const char *dir, const char *sim_name) {
-    // Same two CSV files and row layout as MainWindow::exportLogs (src/mainwindow.cpp:310-368):
-    //   <Scenario>_<box>.csv         one row per run : name;together(step 0);together(step 1);...
-    //   <Scenario>_<box>_detail.csv  five rows per run: name;<phase>;value;value;...
-    return guarded([&] {
-        CBaseParticleSimulator *sim = H(s)->sim;
-        const std::string scenario = sim->m_scenario == DAM_BREAK ? "Dam_break" : "Fountain";
-        char box[32];
-        std::snprintf(box, sizeof(box), "%g", (double)sim->getBoxSize().x());
-        const std::string base = std::string(dir) + "/" + scenario + "_" + box;
-        std::ofstream total(base + ".csv", std::ios::app), detail(base + "_detail.csv", std::ios::app);
-        if (!total || !detail) throw std::runtime_error("gmu_sim_export_logs: cannot open " + base + ".csv");
-        total << sim_name;
-        for (const auto &e : sim->events) total << ";" << e.together();
-        total << "\n";
-        struct Row { const char *name; double sProfilingEvent::*field; };
-        const Row rows[] = {{"Grid", &sProfilingEvent::updateGrid}, {"Density + pressure", &sProfilingEvent::updateDensityPressure},
-                            {"Forces", &sProfilingEvent::updateForces}, {"Collisions", &sProfilingEvent::updateCollisions},
-                            {"Integrate", &sProfilingEvent::integrate}};
-        for (const Row &r : rows) {
-            detail << sim_name << ";" << r.name;
-            for (const auto &e : sim->events) detail << ";" << e.*(r.field);
-            detail << "\n";
-        }
-    });
+    return guarded([&] { exportLogs(*H(s)->sim, dir, sim_name); });
 }
 
 }  // extern "C"

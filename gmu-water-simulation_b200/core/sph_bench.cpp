@@ -11,6 +11,7 @@
 #include <string>
 
 #include "../../include/sph_host.h"
+#include "ExportLogs.h"
 #include "SimulatorFactory.h"
 
 int main(int argc, char **argv) {
@@ -81,10 +82,7 @@ int main(int argc, char **argv) {
                     "\"forces\": %.4f, \"collisions\": %.4f, \"integrate\": %.4f}, \"mirror\": %d, \"brute\": %s}\n",
                     scenario.c_str(), box[0], box[1], box[2], sim->getParticlesCount(), steps, sec, particle_steps / sec,
                     1e3 * sec / steps, ph[0] / ne, ph[1] / ne, ph[2] / ne, ph[3] / ne, ph[4] / ne, mirror, brute ? "true" : "false");
-        if (!csv.empty()) {
-            // sim is owned by `base`; the facade's exporter wants a handle, so write the CSVs here directly
-            std::fprintf(stderr, "csv export: use gmu_sim_export_logs through the facade (bench.py --csv)\n");
-        }
+        if (!csv.empty()) exportLogs(*sim, csv, brute ? "CUDA Brute" : "CUDA Grid");  // needs --phases to have samples
     } catch (const std::exception &e) {
         std::fprintf(stderr, "fatal: %s\n", e.what());
         return 1;
