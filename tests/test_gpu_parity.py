@@ -476,3 +476,37 @@ def test_non_finite_particle_stays_confined(gws, variant):
     o.update_forces(); ctx.forces(); ctx.integrate()
     rec = ctx.download()
     assert np.isfinite(rec["position"][others, :3]).all() and np.isfinite(rec["acceleration"][others, :3]).all()
+
+
+def test_full_size_parity_against_oracle_1m(gws):
+    """The headline workload itself: 1,011,240 particles, 200 steps into the dam break (the benchmarked state).
+    One more step on both sides from the same state: keys, cell ranges, neighbour counts exact; density, pressure,
+    acceleration within rel 1e-5; positions within the acceleration tolerance.  (~15 s of oracle time.)"""
+    box = 3.62
+    sim = gws.Simulator("cuda", box).setup_scene()
+    sim.step_many(200)
+    sim.sync_host()
+    hp = sim.host_particles()
+    assert np.array_equal(hp["id"], np.arange(sim.n, dtype=np.uint32))
+    pos, vel = hp["position"][:, :3].copy(), hp["velocity"][:, :3].copy()
+    o = Oracle(box).set_state(pos, vel)
+    ctx = sim.context()
+    o.update_grid(); ctx.update_grid()
+    assert np.array_equal(ctx.keys(), o.keys())
+    cs, perm = o.cells()
+    assert np.array_equal(ctx.cell_start(), cs)
+    assert np.array_equal(ctx.permutation().astype(np.int32), perm)
+    o.update_density_pressure(); ctx.density_pressure()
+    oc, _ = o.neighbours(lists=False)
+    gc, _ = ctx.neighbours(lists=False)
+    assert np.array_equal(gc, oc) and oc.mean() > 30
+    rho, prs, _ = ctx.density_pressure_accel()
+    check_density(o, rho, prs)
+    o.update_forces(); ctx.forces()
+    check_acc(o.acc_sph, o.acc_scale, ctx.density_pressure_accel()[2])
+    ctx.integrate()
+    rec = ctx.download()
+    tol = pos_tolerance(o)
+    o.integrate()
+    assert np.all(np.abs(rec["position"][:, :3] - o.pos) <= tol)
+    assert ctx.counter("overflow_particles") == 0
