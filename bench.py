@@ -366,6 +366,7 @@ def finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, 
     e2e_sec = max_over_ranks(time.perf_counter() - t0)
     sim.set_mirror_mode(0)
     info = ctx.slab_info()
+    info["far_movers"] = ctx.counter("slab_far_movers")  # particles that crossed > 2 z-layers in a step: must be 0
     infos = [None] * world
     dist.all_gather_object(infos, info)
     if rank == 0:
@@ -377,7 +378,8 @@ def finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, 
             "config": {"workload": workload, "particles": int(total_particles), "box": list(box),
                        "preroll_steps": args.preroll,
                        "parallelism": f"{world} z-slabs, ghost+migration exchange per step via ncclSend/ncclRecv",
-                       "slabs": [{k: i[k] for k in ("z0", "z1", "n_own", "mean_sent_per_step")} for i in infos],
+                       "slabs": [{k: i[k] for k in ("z0", "z1", "n_own", "mean_sent_per_step", "far_movers")} for i in infos],
+                       "particles_conserved": int(sum(i["n_own"] for i in infos)) == WORKLOADS["tank_64M"][1],
                        "l2": "no eviction: the per-GPU working set (GBs) is far larger than the 126 MB L2"},
             "clocks": clocks.summary(),
             "e2e": {"value": total_particles * args.e2e_steps / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": 0,
