@@ -117,6 +117,8 @@ def run_reference(args):
         if WORKLOADS[cand][1] * per_particle_step <= budget:
             name = cand
             break
+    if args.reference_sample:
+        name = args.reference_sample
     box, n = WORKLOADS[name]
     o = Oracle(box).setup_scene()
     o.step(args.warmup)
@@ -405,6 +407,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="dam_break_1M", choices=sorted(WORKLOADS))
+    ap.add_argument("--reference-sample", default=None, choices=sorted(WORKLOADS),
+                    help="--impl reference: force the sampled scene instead of sizing it to the time budget")
     ap.add_argument("--preroll", type=int, default=200)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
