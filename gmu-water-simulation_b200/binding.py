@@ -103,6 +103,7 @@ def cuda_lib():
             "sph_download_particles": (i32, [vp, vp, u32, P(u32)]),
             "sph_particle_count": (i32, [vp, P(u32)]),
             "sph_set_gravity": (i32, [vp, f, f, f]),
+            "sph_set_collision_faces": (i32, [vp, vp, u32]),
             "sph_pin_host_buffer": (i32, [vp, vp, C.c_size_t]),
             "sph_update_grid": (i32, [vp, P(dbl)]),
             "sph_density_pressure": (i32, [vp, P(dbl)]),
@@ -158,6 +159,7 @@ def host_lib():
             "gmu_sim_set_mirror_stride": (i32, [vp, i32]),
             "gmu_sim_sync_host": (i32, [vp]),
             "gmu_sim_set_gravity": (i32, [vp, f, f, f]),
+            "gmu_sim_set_collision_faces": (i32, [vp, vp, i32]),
             "gmu_sim_key": (i32, [vp, i32]),
             "gmu_sim_set_profiling": (i32, [vp, i32, i32]),
             "gmu_sim_set_emission_multiplier": (i32, [vp, i32]),
@@ -301,6 +303,11 @@ class SphContext:
 
     def set_gravity(self, g):
         self._ck(self.lib.sph_set_gravity(self._h, float(g[0]), float(g[1]), float(g[2])))
+
+    def set_collision_faces(self, faces):
+        """faces: (n, 12) float32 = normal, v0, v1, v2 per face (sph_face); an empty array clears the mesh."""
+        faces = np.ascontiguousarray(faces, dtype=np.float32).reshape(-1, 12)
+        self._ck(self.lib.sph_set_collision_faces(self._h, _ptr(faces) if faces.shape[0] else None, faces.shape[0]))
 
     # phases: return device ms when timed=True
     def _phase(self, fn, timed):
@@ -486,6 +493,10 @@ class Simulator:
 
     def set_gravity(self, g):
         self._ck(self.lib.gmu_sim_set_gravity(self._h, float(g[0]), float(g[1]), float(g[2])))
+
+    def set_collision_faces(self, faces):
+        faces = np.ascontiguousarray(faces, dtype=np.float32).reshape(-1, 12)
+        self._ck(self.lib.gmu_sim_set_collision_faces(self._h, _ptr(faces) if faces.shape[0] else None, faces.shape[0]))
 
     def key(self, qt_key):
         self._ck(self.lib.gmu_sim_key(self._h, int(qt_key)))

@@ -67,10 +67,35 @@ void CCUDAParticleSimulator::setupScene() {
     if (!m_slab && m_clParticles.capacity() > 0)
         sph_pin_host_buffer(m_cuda->ctx(), m_clParticles.data(), m_clParticles.capacity() * sizeof(CParticle::Physics));
 
+    pushCollisionFaces();
+
     m_deviceCount = 0;
     m_cuda->check(sph_upload_particles(m_cuda->ctx(), reinterpret_cast<const sph_particle *>(m_clParticles.data()),
                                        (uint32_t)m_particlesCount), "setupScene upload");
     m_deviceCount = (cl_uint)m_particlesCount;
+}
+
+void CCUDAParticleSimulator::setCollisionFaces(const std::vector<sFace> &faces) {
+    m_grid->getCollisionGeometry()->setFaces(faces);
+    if (m_cuda) pushCollisionFaces();
+}
+
+void CCUDAParticleSimulator::pushCollisionFaces() {
+    const auto &faces = m_grid->getCollisionGeometry()->getFaces();
+    std::vector<sph_face> flat(faces.size());
+    for (size_t f = 0; f < faces.size(); ++f) {
+        const sVertex *verts[3] = {&faces[f].m_v0, &faces[f].m_v1, &faces[f].m_v2};
+        float *dst[3] = {flat[f].v0, flat[f].v1, flat[f].v2};
+        flat[f].normal[0] = faces[f].m_normal.x();
+        flat[f].normal[1] = faces[f].m_normal.y();
+        flat[f].normal[2] = faces[f].m_normal.z();
+        for (int v = 0; v < 3; ++v) {
+            dst[v][0] = verts[v]->m_pos.x();
+            dst[v][1] = verts[v]->m_pos.y();
+            dst[v][2] = verts[v]->m_pos.z();
+        }
+    }
+    m_cuda->check(sph_set_collision_faces(m_cuda->ctx(), flat.data(), (uint32_t)flat.size()), "collision faces");
 }
 
 void CCUDAParticleSimulator::pushNewParticles() {

@@ -39,6 +39,8 @@ public:
     // viewer bridge: in Download mode refresh the host mirror only every `stride`-th step (a 60 Hz viewer does not
     // need 1500 read-backs per second); 1 = every step like the reference's OpenCL path
     void setMirrorStride(int stride) { m_mirrorStride = stride < 1 ? 1 : stride; }
+    // collision mesh for CCollisionGeometry::inverseBounce (row f4); may be called before or after setupScene
+    void setCollisionFaces(const std::vector<sFace> &faces);
     void setBruteForce(bool on) { m_brute = on; }          // CGPUBruteParticleSimulator semantics (all pairs)
     // Multi-GPU extension: make this instance rank `rank` of `world` z-slabs (call before setupScene).  ncclId is
     // the 128-byte id from sph_comm_unique_id(), identical on all ranks.  In slab mode the host mirror holds this
@@ -57,6 +59,7 @@ protected:
 
 private:
     void pushNewParticles();
+    void pushCollisionFaces();
 
     bool m_slab = false;
     int m_rank = 0, m_world = 1, m_z0 = 0, m_z1 = 0;

@@ -5,6 +5,11 @@
 // (include/CCollisionGeometry.h:79-120).  Headless, the walls are built from the box size directly;
 // the penalty response itself (inverseBoundingBoxBounce, src/CCollisionGeometry.cpp:117-133) runs on
 // the device, fused into the integration kernel.
+//
+// Faces: the reference also extracts the triangles of the geometry (sVertex/sFace, include/CCollisionGeometry.h:
+// 32-77) for inverseBounce (src/CCollisionGeometry.cpp:97-115), the per-face response "for a general object" that
+// its step never calls.  Headless there is no Qt3D vertex buffer to read, so faces are set explicitly; the response
+// runs on the device next to the wall term (sph_set_collision_faces).
 #pragma once
 
 #include <vector>
@@ -20,6 +25,22 @@ struct sWall {
     cl_float3 position;
 };
 static_assert(sizeof(sWall) == 32, "sWall must stay 32 bytes");
+
+struct sVertex {
+    QVector3D m_pos, m_normal;
+    sVertex() = default;
+    explicit sVertex(QVector3D pos) : m_pos(pos) {}
+    sVertex(QVector3D pos, QVector3D normal) : m_pos(pos), m_normal(normal) {}
+};
+
+struct sFace {
+    sVertex m_v0, m_v1, m_v2;
+    QVector3D m_normal;
+    sFace() = default;
+    // as in the reference: without an explicit normal the face takes the normal of its first vertex
+    sFace(sVertex v0, sVertex v1, sVertex v2) : m_v0(v0), m_v1(v1), m_v2(v2), m_normal(v0.m_normal) {}
+    sFace(sVertex v0, sVertex v1, sVertex v2, QVector3D normal) : m_v0(v0), m_v1(v1), m_v2(v2), m_normal(normal) {}
+};
 
 struct sBoundingBox {
     QVector3D m_min, m_max;
@@ -43,7 +64,10 @@ public:
         }
     }
     const sBoundingBox &getBoundingBox() const { return m_box; }
+    const std::vector<sFace> &getFaces() const { return m_faces; }
+    void setFaces(std::vector<sFace> faces) { m_faces = std::move(faces); }
 
 private:
     sBoundingBox m_box;
+    std::vector<sFace> m_faces;
 };

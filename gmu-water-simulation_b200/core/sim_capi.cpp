@@ -140,6 +140,19 @@ int gmu_sim_set_gravity(gmu_sim *s, float gx, float gy, float gz) {
     return guarded([&] { H(s)->sim->setGravityVector(QVector3D(gx, gy, gz)); });
 }
 
+int gmu_sim_set_collision_faces(gmu_sim *s, const float *f, int n_faces) {
+    return guarded([&] {
+        if (!H(s)->cuda) throw std::runtime_error("gmu_sim_set_collision_faces: not a CUDA simulator");
+        std::vector<sFace> faces;
+        for (int k = 0; k < n_faces; ++k, f += 12) {
+            const QVector3D normal(f[0], f[1], f[2]);
+            faces.emplace_back(sVertex(QVector3D(f[3], f[4], f[5]), normal), sVertex(QVector3D(f[6], f[7], f[8]), normal),
+                               sVertex(QVector3D(f[9], f[10], f[11]), normal));  // the face takes its first vertex's normal
+        }
+        H(s)->cuda->setCollisionFaces(faces);
+    });
+}
+
 int gmu_sim_key(gmu_sim *s, int qt_key) { return guarded([&] { H(s)->sim->onKeyPressed((Qt::Key)qt_key); }); }
 
 int gmu_sim_set_profiling(gmu_sim *s, int on, int stride) {

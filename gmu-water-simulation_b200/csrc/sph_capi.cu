@@ -57,6 +57,7 @@ struct sph_context {
     uint64_t kernel_launches = 0, graph_launches = 0, steps = 0;
     std::string err;
     void *pinned_ptr = nullptr;
+    float4 *d_mesh_planes = nullptr;  // sph_set_collision_faces
     // bench hygiene: evict L2 between timed steps (option "flush_l2") and time each step separately
     int opt_flush_l2 = 0;
     float4 *d_flush = nullptr;
@@ -574,6 +575,7 @@ int sph_destroy(sph_context *c) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->d_flush) cudaFree(c->d_flush);
+    if (c->d_mesh_planes) cudaFree(c->d_mesh_planes);
     slab_release(c);
     for (cudaEvent_t e : c->step_events) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -748,6 +750,47 @@ int sph_set_gravity(sph_context *c, float gx, float gy, float gz) {
     c->cfg.gravity[1] = c->P.gy = gy;
     c->cfg.gravity[2] = c->P.gz = gz;
     drop_graph(c);  // kernel parameters are baked into the graph
+    return SPH_OK;
+}
+
+int sph_set_collision_faces(sph_context *c, const sph_face *faces, uint32_t n_faces) {
+    REQUIRE(c, c && (faces || n_faces == 0), SPH_ERR_ARGUMENT, "sph_set_collision_faces: NULL argument");
+    REQUIRE(c, n_faces <= (1u << 20), SPH_ERR_ARGUMENT, "sph_set_collision_faces: more than 2^20 faces");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    drop_graph(c);
+    if (c->d_mesh_planes) {
+        cudaFree(c->d_mesh_planes);
+        c->d_mesh_planes = nullptr;
+    }
+    c->P.mesh_planes = nullptr;
+    c->P.mesh_plane_count = 0;
+    c->P.mesh_k_f = (float)5000.0;  // src/CCollisionGeometry.cpp:109
+    if (n_faces == 0) return SPH_OK;
+    // The per-face part of inverseBounce is hoisted out of the particle loop: inverseNormal = normal * (-1), then
+    // QVector3D::normalize() as Qt 5 defines it (fp64 squared length, early-out when it is fuzzily 1 or 0, fp64
+    // division by the root, narrowed per component).
+    std::vector<float4> planes;
+    planes.reserve((size_t)n_faces * 6);
+    for (uint32_t f = 0; f < n_faces; ++f) {
+        float nx = faces[f].normal[0] * -1.0f, ny = faces[f].normal[1] * -1.0f, nz = faces[f].normal[2] * -1.0f;
+        double len = (double)nx * (double)nx + (double)ny * (double)ny + (double)nz * (double)nz;
+        if (!(std::fabs(len - 1.0f) <= 0.000000000001 || std::fabs(len) <= 0.000000000001)) {
+            len = std::sqrt(len);
+            nx = (float)((double)nx / len);
+            ny = (float)((double)ny / len);
+            nz = (float)((double)nz / len);
+        }
+        const float *verts[3] = {faces[f].v0, faces[f].v1, faces[f].v2};
+        for (const float *v : verts) {
+            planes.push_back(make_float4(nx, ny, nz, 0.f));
+            planes.push_back(make_float4(v[0], v[1], v[2], 0.f));
+        }
+    }
+    CUDA_TRY(c, dalloc(&c->d_mesh_planes, planes.size()));
+    CUDA_TRY(c, cudaMemcpy(c->d_mesh_planes, planes.data(), planes.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    c->P.mesh_planes = c->d_mesh_planes;
+    c->P.mesh_plane_count = (int)(planes.size() / 2);
     return SPH_OK;
 }
 

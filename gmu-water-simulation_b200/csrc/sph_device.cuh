@@ -40,6 +40,11 @@ struct Params {
     double wall_damping_d, wall_skin_d;
     int wall_count;
     WallDev walls[6];
+    // optional collision mesh (sph_set_collision_faces): plane k = {planes[2k] = inverse unit normal, planes[2k+1] =
+    // vertex}, three planes per face in face/vertex order; 0 planes = the shipped behaviour
+    const float4 *mesh_planes;
+    int mesh_plane_count;
+    float mesh_k_f;  // float(5000.0)
 };
 
 // (dx*dx + dy*dy) + dz*dz with one rounding per operation — QVector3D::lengthSquared on a build
@@ -187,6 +192,29 @@ __device__ __forceinline__ void walls_and_integrate(const float4 p, const float4
     a.x = __fadd_rn(a.x, wx);
     a.y = __fadd_rn(a.y, wy);
     a.z = __fadd_rn(a.z, wz);
+    if (P.mesh_plane_count > 0) {
+        // CCollisionGeometry::inverseBounce (src/CCollisionGeometry.cpp:97-115): same shape as the wall term, one
+        // plane per face vertex, spring 5000.0 and the literals -0.9 / 0.01; its own accumulator starts at 0
+        float mx = 0.f, my = 0.f, mz = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < P.mesh_plane_count; ++k) {
+            const float4 in = __ldg(P.mesh_planes + 2 * k), q = __ldg(P.mesh_planes + 2 * k + 1);
+            const double d = __dadd_rn((double)dot_exact(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z), in.x, in.y, in.z), 0.01);
+            if (d > 0.0) {
+                const float df = (float)d;
+                mx = __fadd_rn(mx, __fmul_rn(__fmul_rn(P.mesh_k_f, in.x), df));
+                my = __fadd_rn(my, __fmul_rn(__fmul_rn(P.mesh_k_f, in.y), df));
+                mz = __fadd_rn(mz, __fmul_rn(__fmul_rn(P.mesh_k_f, in.z), df));
+                const float s = (float)__dmul_rn(-0.9, (double)dot_exact(v.x, v.y, v.z, in.x, in.y, in.z));
+                mx = __fadd_rn(mx, __fmul_rn(s, in.x));
+                my = __fadd_rn(my, __fmul_rn(s, in.y));
+                mz = __fadd_rn(mz, __fmul_rn(s, in.z));
+            }
+        }
+        a.x = __fadd_rn(a.x, mx);
+        a.y = __fadd_rn(a.y, my);
+        a.z = __fadd_rn(a.z, mz);
+    }
     const float dt = P.dt;
     np.x = __fadd_rn(__fadd_rn(p.x, __fmul_rn(v.x, dt)), __fmul_rn(__fmul_rn(a.x, dt), dt));
     np.y = __fadd_rn(__fadd_rn(p.y, __fmul_rn(v.y, dt)), __fmul_rn(__fmul_rn(a.y, dt), dt));

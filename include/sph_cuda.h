@@ -110,6 +110,17 @@ int sph_download_particles(sph_context *ctx, sph_particle *aos, uint32_t capacit
 int sph_particle_count(const sph_context *ctx, uint32_t *n_out);
 /* ≙ CGPUBaseParticleSimulator::setGravityVector, src/CGPUBaseParticleSimulator.cpp:11-15 */
 int sph_set_gravity(sph_context *ctx, float gx, float gy, float gz);
+/* Collision mesh for CCollisionGeometry::inverseBounce (src/CCollisionGeometry.cpp:97-115; sFace,
+ * include/CCollisionGeometry.h:46-77).  The reference prepared this per-face bounce for "collisions with a general
+ * object" but its step never calls it; with n_faces > 0 the force phase adds inverseBounce(position, velocity)
+ * after the bounding-box term, n_faces = 0 restores the shipped behaviour.  Every vertex of every face acts as a
+ * plane with the face's normal (negated and normalised like QVector3D::normalize), spring 5000.0, damping -0.9,
+ * skin 0.01 — the literals of the reference. */
+typedef struct sph_face {
+    float normal[3];
+    float v0[3], v1[3], v2[3];
+} sph_face; /* 48 bytes */
+int sph_set_collision_faces(sph_context *ctx, const sph_face *faces, uint32_t n_faces);
 /* Page-lock the caller's host mirror once (m_clParticles is reserved up front, src/CBaseParticleSimulator.cpp:42)
  * so per-step uploads/downloads run at full PCIe speed; unpinned again by sph_destroy. */
 int sph_pin_host_buffer(sph_context *ctx, void *ptr, size_t bytes);

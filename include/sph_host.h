@@ -36,6 +36,8 @@ int gmu_sim_set_mirror_stride(gmu_sim *s, int stride);              /* download 
 int gmu_sim_sync_host(gmu_sim *s);                                 /* device -> host mirror */
 int gmu_sim_set_gravity(gmu_sim *s, float gx, float gy, float gz); /* setGravityVector */
 int gmu_sim_key(gmu_sim *s, int qt_key);                           /* onKeyPressed */
+/* collision mesh for CCollisionGeometry::inverseBounce: n faces x 12 floats (normal, v0, v1, v2); 0 clears it */
+int gmu_sim_set_collision_faces(gmu_sim *s, const float *faces12, int n_faces);
 int gmu_sim_set_profiling(gmu_sim *s, int on, int stride);
 int gmu_sim_set_emission_multiplier(gmu_sim *s, int nozzles);
 uint64_t gmu_sim_particle_count(gmu_sim *s);

@@ -59,6 +59,22 @@ struct Wall {  // include/CCollisionGeometry.h:23-30
     V3 normal, position;
 };
 
+struct Face {  // include/CCollisionGeometry.h:46-77 (sFace: three vertices and one normal)
+    V3 normal, v[3];
+};
+
+// QVector3D::normalize() of Qt 5 (qvector3d.cpp; Qt is a third-party dependency, version unpinned): squared
+// length in fp64; returns unchanged if qFuzzyIsNull(len - 1.0f) or qFuzzyIsNull(len) (|d| <= 1e-12); else every
+// component is divided in fp64 by sqrt(len) and narrowed.
+inline void qt_normalize(V3 &a) {
+    double len = (double)a.x * (double)a.x + (double)a.y * (double)a.y + (double)a.z * (double)a.z;
+    if (std::fabs(len - 1.0f) <= 0.000000000001 || std::fabs(len) <= 0.000000000001) return;
+    len = std::sqrt(len);
+    a.x = (float)((double)a.x / len);
+    a.y = (float)((double)a.y / len);
+    a.z = (float)((double)a.z / len);
+}
+
 double now_ms() {
     using clk = std::chrono::steady_clock;
     return std::chrono::duration<double, std::milli>(clk::now().time_since_epoch()).count();
@@ -75,11 +91,12 @@ struct OracleSim {
     int res[3];
     int64_t max_count = 0;
     // per particle (index == id, as in m_clParticles / CParticle)
-    std::vector<V3> pos, vel, acc, acc_sph, acc_wall;
+    std::vector<V3> pos, vel, acc, acc_sph, acc_wall, acc_mesh;
     std::vector<float> density, pressure, acc_scale;
     // CGrid: one vector of particle ids per cell (include/CGrid.h:24-28, src/CGrid.cpp:17-18)
     std::vector<std::vector<int32_t>> cells;
     Wall walls[6];
+    std::vector<Face> faces;  // optional collision mesh (row f4); empty = the shipped behaviour
     int threads = 1;  // 1 = the reference's behaviour (single-threaded); > 1 only for the labelled all-cores baseline
     // kernel coefficients, function-local statics in the reference (src/CCPUParticleSimulator.cpp:11,19,26)
     double poly6, spiky, visc, h_squared;
@@ -113,6 +130,27 @@ struct OracleSim {
                 V3 damp = (float)(kWallDamping * (double)dot(v, inv)) * inv;
                 a += damp;
                 if (scale) *scale += std::sqrt((double)length_squared(spring)) + std::sqrt((double)length_squared(damp));
+            }
+        }
+        return a;
+    }
+
+    // src/CCollisionGeometry.cpp:97-115 — the per-face bounce the reference prepared for "collisions with a general
+    // object" but never calls: every vertex of every face is a plane with the face normal, spring 5000.0.
+    V3 mesh_bounce(const V3 &p, const V3 &v, double *scale) const {
+        V3 a(0, 0, 0);
+        for (const Face &f : faces) {
+            for (const V3 &vertex : f.v) {
+                V3 inv = f.normal * (-1.0f);
+                qt_normalize(inv);
+                double d = (double)dot(vertex - p, inv) + 0.01;
+                if (d > 0.0) {
+                    V3 spring = ((float)5000.0 * inv) * (float)d;
+                    a += spring;
+                    V3 damp = (float)(-0.9 * (double)dot(v, inv)) * inv;
+                    a += damp;
+                    if (scale) *scale += std::sqrt((double)length_squared(spring)) + std::sqrt((double)length_squared(damp));
+                }
             }
         }
         return a;
@@ -158,6 +196,7 @@ void oracle_add_particle(OracleSim *s, float x, float y, float z, float vx, floa
     s->acc.emplace_back(0.0f, 0.0f, 0.0f);
     s->acc_sph.emplace_back(0.0f, 0.0f, 0.0f);
     s->acc_wall.emplace_back(0.0f, 0.0f, 0.0f);
+    s->acc_mesh.emplace_back(0.0f, 0.0f, 0.0f);
     s->acc_scale.push_back(0.0f);
     s->density.push_back(0.0f);
     s->pressure.push_back(0.0f);
@@ -190,7 +229,7 @@ void oracle_setup_scene(OracleSim *s) {
 
 void oracle_set_state(OracleSim *s, int64_t n, const float *pos, const float *vel) {
     for (auto &c : s->cells) c.clear();
-    s->pos.clear(); s->vel.clear(); s->acc.clear(); s->acc_sph.clear(); s->acc_wall.clear();
+    s->pos.clear(); s->vel.clear(); s->acc.clear(); s->acc_sph.clear(); s->acc_wall.clear(); s->acc_mesh.clear();
     s->acc_scale.clear(); s->density.clear(); s->pressure.clear();
     for (int64_t i = 0; i < n; ++i)
         oracle_add_particle(s, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]);
@@ -198,6 +237,17 @@ void oracle_set_state(OracleSim *s, int64_t n, const float *pos, const float *ve
 }
 
 void oracle_set_gravity(OracleSim *s, float gx, float gy, float gz) { s->gravity = V3(gx, gy, gz); }
+
+void oracle_set_faces(OracleSim *s, int n, const float *f) {
+    s->faces.clear();
+    std::fill(s->acc_mesh.begin(), s->acc_mesh.end(), V3());
+    for (int k = 0; k < n; ++k, f += 12) {
+        Face face;
+        face.normal = V3(f[0], f[1], f[2]);
+        for (int v = 0; v < 3; ++v) face.v[v] = V3(f[3 + 3 * v], f[4 + 3 * v], f[5 + 3 * v]);
+        s->faces.push_back(face);
+    }
+}
 
 int oracle_set_threads(OracleSim *s, int threads) {
     if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
@@ -354,6 +404,13 @@ static inline void force_finish(OracleSim *s, int32_t i, ForceAcc &fa) {
     const V3 wall = s->wall_bounce(s->pos[i], s->vel[i], &scale);
     s->acc_wall[i] = wall;
     a += wall;
+    // extension point (row f4): the reference never calls inverseBounce; with a mesh set, its result is added the
+    // same way the bounding-box term is (`acceleration() += ...`, src/CCPUParticleSimulator.cpp:196)
+    if (!s->faces.empty()) {
+        const V3 mesh = s->mesh_bounce(s->pos[i], s->vel[i], &scale);
+        s->acc_mesh[i] = mesh;
+        a += mesh;
+    }
     s->acc[i] = a;
     s->acc_scale[i] = (float)scale;
 }
@@ -435,6 +492,7 @@ void oracle_get_vel(const OracleSim *s, float *o) { copy3(s->vel, o); }
 void oracle_get_acc(const OracleSim *s, float *o) { copy3(s->acc, o); }
 void oracle_get_acc_sph(const OracleSim *s, float *o) { copy3(s->acc_sph, o); }
 void oracle_get_acc_wall(const OracleSim *s, float *o) { copy3(s->acc_wall, o); }
+void oracle_get_acc_mesh(const OracleSim *s, float *o) { copy3(s->acc_mesh, o); }
 void oracle_get_acc_scale(const OracleSim *s, float *o) { std::memcpy(o, s->acc_scale.data(), s->acc_scale.size() * sizeof(float)); }
 void oracle_get_density(const OracleSim *s, float *o) { std::memcpy(o, s->density.data(), s->density.size() * sizeof(float)); }
 void oracle_get_pressure(const OracleSim *s, float *o) { std::memcpy(o, s->pressure.data(), s->pressure.size() * sizeof(float)); }

@@ -41,6 +41,10 @@ void oracle_set_state(OracleSim *s, int64_t n, const float *pos, const float *ve
 /* addParticle (src/CBaseParticleSimulator.cpp:67-74) */
 void oracle_add_particle(OracleSim *s, float x, float y, float z, float vx, float vy, float vz);
 void oracle_set_gravity(OracleSim *s, float gx, float gy, float gz);
+/* collision mesh for CCollisionGeometry::inverseBounce (src/CCollisionGeometry.cpp:97-115), which the reference
+ * prepared but never calls: n faces, 12 floats each = normal xyz, v0 xyz, v1 xyz, v2 xyz.  With n > 0 the force
+ * phase adds inverseBounce(position, velocity) after the bounding-box term; n = 0 restores the shipped behaviour. */
+void oracle_set_faces(OracleSim *s, int n, const float *faces12);
 /* NOT reference behaviour (the reference CPU path is single-threaded): run the density and force loops on `threads`
  * std::threads (<= 0: all cores) for the labelled all-cores baseline; results stay bit-identical. Returns the count used. */
 int oracle_set_threads(OracleSim *s, int threads);
@@ -72,6 +76,7 @@ void oracle_get_vel(const OracleSim *s, float *out3n);
 void oracle_get_acc(const OracleSim *s, float *out3n);       /* SPH + wall term (what updateForces leaves) */
 void oracle_get_acc_sph(const OracleSim *s, float *out3n);   /* before the wall term is added */
 void oracle_get_acc_wall(const OracleSim *s, float *out3n);  /* the wall term alone (inverseBoundingBoxBounce) */
+void oracle_get_acc_mesh(const OracleSim *s, float *out3n);  /* the mesh term alone (inverseBounce); zero without faces */
 void oracle_get_acc_scale(const OracleSim *s, float *outn);  /* sum of |terms| / rho: conditioning scale for tolerances */
 void oracle_get_density(const OracleSim *s, float *outn);
 void oracle_get_pressure(const OracleSim *s, float *outn);

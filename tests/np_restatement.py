@@ -60,6 +60,13 @@ class NpSim:
             ([f32(1), z, z], [mx[0], z, z]), ([z, f32(1), z], [z, mx[1], z]), ([z, z, f32(1)], [z, z, mx[2]]),
         ]
 
+        self.faces = []  # (normal, [v0, v1, v2]) — optional collision mesh, unused by the reference's own step
+
+    def set_faces(self, faces12):
+        self.faces = []
+        for f in np.asarray(faces12, dtype=np.float32).reshape(-1, 12):
+            self.faces.append(([f32(c) for c in f[0:3]], [[f32(c) for c in f[3 + 3 * v:6 + 3 * v]] for v in range(3)]))
+
     def cell(self, x, y, z):
         return self.cells.setdefault((x, y, z), [])
 
@@ -156,6 +163,25 @@ class NpSim:
                 acc = vadd(acc, vmul(inv, WALL_DAMPING * float(dot(v, inv))))
         return acc
 
+    @staticmethod
+    def qt_normalized(a):  # QVector3D::normalize() of Qt 5 (third-party; restated from its published source)
+        ln = float(a[0]) * float(a[0]) + float(a[1]) * float(a[1]) + float(a[2]) * float(a[2])
+        if abs(ln - 1.0) <= 1e-12 or abs(ln) <= 1e-12:
+            return list(a)
+        ln = math.sqrt(ln)
+        return [f32(float(c) / ln) for c in a]
+
+    def mesh_bounce(self, p, v):  # src/CCollisionGeometry.cpp:97-115
+        acc = [f32(0)] * 3
+        for normal, verts in self.faces:
+            for q in verts:
+                inv = self.qt_normalized(vmul(normal, -1.0))
+                d = float(dot(vsub(q, p), inv)) + 0.01
+                if d > 0.0:
+                    acc = vadd(acc, vmul(vmul(inv, 5000.0), d))
+                    acc = vadd(acc, vmul(inv, -0.9 * float(dot(v, inv))))
+        return acc
+
     def forces(self):  # src/CCPUParticleSimulator.cpp:143-203
         for x, y, z, i in self.each_particle():
             fg = vmul(self.gravity, self.rho[i])
@@ -173,7 +199,10 @@ class NpSim:
             fp = vmul(fp, f32(-MASS * self.rho[i]))
             fv = vmul(fv, f32(VISCOSITY * MASS))
             a = vdiv(vadd(vadd(fp, fv), fg), self.rho[i])
-            self.acc[i] = vadd(a, self.wall_bounce(self.pos[i], self.vel[i]))
+            a = vadd(a, self.wall_bounce(self.pos[i], self.vel[i]))
+            if self.faces:  # extension point: inverseBounce added the way the bounding-box term is
+                a = vadd(a, self.mesh_bounce(self.pos[i], self.vel[i]))
+            self.acc[i] = a
 
     def integrate(self):  # src/CCPUParticleSimulator.cpp:211-229
         for i in range(len(self.pos)):

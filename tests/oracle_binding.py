@@ -33,6 +33,7 @@ def _load():
         "oracle_set_state": (None, [vp, i64, vp, vp]),
         "oracle_add_particle": (None, [vp, f, f, f, f, f, f]),
         "oracle_set_gravity": (None, [vp, f, f, f]),
+        "oracle_set_faces": (None, [vp, i32, vp]),
         "oracle_set_threads": (i32, [vp, i32]),
         "oracle_generate_particles": (i32, [vp]),
         "oracle_update_grid": (d, [vp]),
@@ -52,6 +53,7 @@ def _load():
         "oracle_get_acc": (None, [vp, vp]),
         "oracle_get_acc_sph": (None, [vp, vp]),
         "oracle_get_acc_wall": (None, [vp, vp]),
+        "oracle_get_acc_mesh": (None, [vp, vp]),
         "oracle_get_acc_scale": (None, [vp, vp]),
         "oracle_get_density": (None, [vp, vp]),
         "oracle_get_pressure": (None, [vp, vp]),
@@ -111,6 +113,11 @@ class Oracle:
 
     def set_gravity(self, g):
         lib().oracle_set_gravity(self._h, *[float(v) for v in g])
+
+    def set_faces(self, faces):
+        """(n, 12) float32: normal, v0, v1, v2 per face; empty clears the mesh (shipped behaviour)."""
+        faces = np.ascontiguousarray(faces, dtype=np.float32).reshape(-1, 12)
+        lib().oracle_set_faces(self._h, faces.shape[0], _p(faces) if faces.shape[0] else None)
 
     def set_threads(self, threads=0):
         """NOT reference behaviour: worker threads for the labelled all-cores baseline (0 = all cores)."""
@@ -181,6 +188,7 @@ class Oracle:
     acc = property(lambda self: self._vec("oracle_get_acc", 3))
     acc_sph = property(lambda self: self._vec("oracle_get_acc_sph", 3))
     acc_wall = property(lambda self: self._vec("oracle_get_acc_wall", 3))
+    acc_mesh = property(lambda self: self._vec("oracle_get_acc_mesh", 3))
     acc_scale = property(lambda self: self._vec("oracle_get_acc_scale", 1))
     density = property(lambda self: self._vec("oracle_get_density", 1))
     pressure = property(lambda self: self._vec("oracle_get_pressure", 1))
