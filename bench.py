@@ -260,6 +260,7 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for _ in range(reps):
         flush.zero_()
+        flush.view(torch.int32).sum()  # read-back: leaves clean scratch lines, no write-backs inside the timed phases
         torch.cuda.synchronize()
         phase_ms["grid"] += ctx.update_grid()
         phase_ms["density"] += ctx.density_pressure()
@@ -338,7 +339,7 @@ def run_ours(args):
             "config": {"workload": workload, "particles_per_gpu": n, "box": list(box), "grid": grid_res,
                        "preroll_steps": args.preroll, "mean_neighbours": mean_nb,
                        "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (slab mode pending)",
-                       "l2": "L2 evicted (256 MiB scratch write) before every timed step" if args.flush_l2 else "no eviction"},
+                       "l2": "L2 evicted (256 MiB scratch write, then read back so that no dirty scratch lines remain) before every timed step" if args.flush_l2 else "no eviction"},
             "clocks": clocks.summary(),
             "e2e": e2e,
             "gpu_launches": int(launches),

@@ -9,7 +9,8 @@
 //   K2 scan          : single-pass decoupled look-back exclusive scan of count -> cell_start (8192 cells per tile),
 //                      zeroes count for the next step
 //   K3 bucket        : slot = cell_start[key] + off  ->  bucket_src/bucket_id   (arrival order)
-//   K4 rank_scatter  : rank inside the cell by particle id, gather pos/vel into canonical order
+//   K4 rank_scatter  : rank inside the cell by particle id, gather pos/vel into canonical order; also re-arms the
+//                      scan's look-back words and the overflow list for the next use (no memset nodes in the step)
 #include "sph_kernels.h"
 
 namespace sph {
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(512) k_scan(int *__restrict__ count, int *__re
 }
 
 void launch_scan(const GridBuffers &g, cudaStream_t st) {
-    cudaMemsetAsync(g.scan_status, 0, sizeof(unsigned long long) * (size_t)(g.n_tiles + 1), st);
+    // scan_status is all zero here: zeroed at creation and again by every k_rank_scatter (which follows each scan)
     k_scan<<<g.n_tiles, 512, 0, st>>>(g.count, g.cell_start, g.n_scan_items, g.scan_status, g.n_tiles);
 }
 
@@ -158,8 +159,14 @@ __global__ void __launch_bounds__(256) k_rank_scatter(const float4 *__restrict__
                                                       const int *__restrict__ cell_start,
                                                       const int *__restrict__ bucket_src,
                                                       const int *__restrict__ bucket_id, float *__restrict__ xs,
-                                                      float *__restrict__ ys, float *__restrict__ zs) {
+                                                      float *__restrict__ ys, float *__restrict__ zs,
+                                                      unsigned long long *__restrict__ scan_status, int n_status,
+                                                      int *__restrict__ ovf) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    // housekeeping that used to be two memset nodes: the scan of this grid build is complete (stream order), and
+    // the overflow list of the previous density pass has been consumed
+    if (s < n_status) scan_status[s] = 0ull;
+    if (s == 0 && ovf) ovf[0] = 0;
     if (s >= n) {
         // sentinel tail: the 4-wide candidate loads may run up to 3 entries past the last particle
         if (xs && s < n + kSoaPad) xs[s] = ys[s] = zs[s] = 1.0e18f;
@@ -189,9 +196,11 @@ __global__ void __launch_bounds__(256) k_rank_scatter(const float4 *__restrict__
 
 void launch_rank_scatter(const float4 *pos_a, const float4 *vel_a, float4 *pos_s, float4 *vel_s, int n,
                          const GridBuffers &g, const NbBuffers &nb, cudaStream_t st) {
-    if (n <= 0) return;
-    k_rank_scatter<<<(n + kSoaPad + 255) / 256, 256, 0, st>>>(pos_a, vel_a, pos_s, vel_s, g.key_s, n, g.key_a,
-                                                              g.cell_start, g.bucket_src, g.bucket_id, nb.xs, nb.ys, nb.zs);
+    if (n < 0) n = 0;
+    const int threads = (n + kSoaPad > g.n_tiles + 1) ? n + kSoaPad : g.n_tiles + 1;
+    k_rank_scatter<<<(threads + 255) / 256, 256, 0, st>>>(pos_a, vel_a, pos_s, vel_s, g.key_s, n, g.key_a, g.cell_start,
+                                                          g.bucket_src, g.bucket_id, nb.xs, nb.ys, nb.zs, g.scan_status,
+                                                          g.n_tiles + 1, nb.ovf);
 }
 
 }  // namespace sph

@@ -46,7 +46,7 @@ void launch_density(const float4 *pos_s, const int *key_s, const int *cell_start
 void launch_forces(const float4 *pos_s, const float4 *vel_s, const float4 *dp, const int *key_s, const int *cell_start,
                    float4 *acc, int n, const Params &P, int variant, cudaStream_t st);
 void launch_density_mask(const NbBuffers &nb, const float4 *vel_s, const int *key_s, const int *cell_start, float4 *dp,
-                         int *nb_count, int n, const Params &P, cudaStream_t st);
+                         int *nb_count, int n, const Params &P, cudaStream_t st, bool reset_overflow_list);
 // [i0, i1) = index range of the canonical order to process (the whole array outside slab mode)
 // pos_out != NULL: fused with the wall term + integration (new state written to pos_out/vel_out, pos_s supplies the ids)
 void launch_forces_mask(const NbBuffers &nb, const float4 *dp, const int *nb_count, const int *key_s, const int *cell_start,

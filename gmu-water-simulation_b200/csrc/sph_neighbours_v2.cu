@@ -243,9 +243,10 @@ __global__ void __launch_bounds__(128, 8) k_density_mask(const float *__restrict
 }
 
 void launch_density_mask(const NbBuffers &nb, const float4 *vel_s, const int *key_s, const int *cell_start, float4 *dp,
-                         int *nb_count, int n, const Params &P, cudaStream_t st) {
+                         int *nb_count, int n, const Params &P, cudaStream_t st, bool reset_overflow_list) {
     if (n <= 0) return;
-    cudaMemsetAsync(nb.ovf, 0, sizeof(int), st);
+    // k_rank_scatter leaves the list empty; only a second density pass on the same grid needs the explicit reset
+    if (reset_overflow_list) cudaMemsetAsync(nb.ovf, 0, sizeof(int), st);
     if (P.tuning & 2)
         k_density_mask<true><<<(n + 127) / 128, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, vel_s, key_s, cell_start, dp, nb.fdat,
                                                               nb.mask, nb_count, nb.words, nb.ovf, n, P);
