@@ -10,7 +10,7 @@ SMI=$!
 python bench.py --steps 200 --warmup 10 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 kill $SMI
 # launch list of the same command (shorter timed region; 200 pre-roll steps x 8 kernels are skipped)
-ncu --metrics gpu__time_duration.sum --clock-control none -s 1450 -c 260 --csv --log-file gpurun_out/${TAG}_launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 1450 -c 270 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 30 --warmup 5 --e2e-steps 2 --no-cpu-baseline --no-scaling-baseline > gpurun_out/${TAG}_bench_under_ncu.json 2>&1
 # full sections for the two dominant kernels (step 201)
 ncu --set full --clock-control none --import-source on -k regex:"k_density_mask|k_forces_mask" -s 400 -c 2 -o gpurun_out/${TAG}_neighbour_kernels \

@@ -26,6 +26,11 @@ rng = np.random.default_rng(1)
 pos = (rng.random((1500, 3), dtype=np.float32) - 0.5) * np.float32(0.03)
 c2 = gws.SphContext(0.4, 1500); c2.upload(gws.particles_from_arrays(pos)); c2.step(2)
 print("overflow particles", c2.counter("overflow_particles"))
+# collision mesh (planes looped in the fused epilogue and in k_integrate_collide), second density pass on one grid
+b = np.float32(0.2)
+face = [-0.5, -0.5, 0.0, -b + 0.04, -b, -b, -b, -b + 0.04, -b, -b + 0.04, -b, b]
+m = gws.Simulator("cuda", 0.4).setup_scene(); m.set_collision_faces(np.array([face], dtype=np.float32)); m.step_many(4)
+mc = m.context(); mc.update_grid(); mc.density_pressure(); mc.density_pressure(); mc.forces(); mc.integrate()
 # fountain (append) and single-rank slab mode (pack kernel, range launches)
 f = gws.Simulator("cuda", 0.4, scenario=gws.FOUNTAIN).setup_scene(); f.step(20)
 s = gws.Simulator("cuda", (0.4, 0.4, 0.9)).enable_slab(0, 1, bytes(128)).setup_scene(); s.step_many(5)
