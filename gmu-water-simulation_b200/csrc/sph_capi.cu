@@ -126,6 +126,8 @@ Params make_params(const sph_config &c) {
     P.h_win = (double)c.h * (1.0 + 1e-6);
     P.rz_global = P.rz;
     P.z_base = 0;
+    P.own_z0 = 0;
+    P.own_z1 = P.rz;
     // src/CCPUParticleSimulator.cpp:46-48: m_boxSize.x() / 2.0 and CParticle::h widen to double
     P.hbx = (double)c.box[0] / 2.0;
     P.hby = (double)c.box[1] / 2.0;
@@ -1162,7 +1164,7 @@ int sph_get_counter(const sph_context *c, const char *name, uint64_t *value) {
         cudaMemcpy(&v, c->nb.ovf, sizeof(int), cudaMemcpyDeviceToHost);
         *value = (uint64_t)v;
     }
-    else if (k == "slab_far_movers") {  // particles that crossed more than 2 z-layers in one step (must stay 0)
+    else if (k == "slab_far_movers") {  // particles the boundary-only exchange would have missed (must stay 0)
         int v = 0;
         if (c->slab) cudaMemcpy(&v, c->slab->d_counters + 4, sizeof(int), cudaMemcpyDeviceToHost);
         *value = (uint64_t)v;
@@ -1210,6 +1212,8 @@ int sph_slab_create(const sph_config *cfg, sph_context **out) {
     c->cfg = *cfg;
     c->P.rz_global = cfg->grid_res[2];
     c->P.z_base = z_base;
+    c->P.own_z0 = z0;
+    c->P.own_z1 = z1;
     c->opt_use_graph = 0;  // the particle count changes every step
     Slab *s = new Slab();
     c->slab = s;

@@ -25,6 +25,7 @@ struct Params {
     double h_win;         // h (1 + 1e-6): half-width of the candidate x-window
     int rz_global;        // z resolution of the whole tank (== rz on a single device)
     int z_base;           // slab mode: global index of local z-layer 0 (0 on a single device)
+    int own_z0, own_z1;   // slab mode: owned global layers [own_z0, own_z1) (0 and rz_global on a single device)
     double hbx, hby, hbz; // double(box)/2.0           (src/CCPUParticleSimulator.cpp:46-48)
     double h_d;           // double(h)
     float h, h2;          // h2 = fl32(h*h) == 0x3b08df0c
@@ -158,6 +159,15 @@ __device__ __forceinline__ void for_each_window_slot(float px, int key, const in
             f((dz + 1) * 3 + (dy + 1), a, b);
         }
     }
+}
+
+// Slab mode: the overlapped exchange packs only the four owned layers next to each interior face (two that become
+// the neighbour's ghosts plus two of slack).  A particle that starts further inside and ends the step in the outer
+// two layers or beyond would be missed as a ghost / migrant; such particles are counted ("slab_far_movers") and the
+// count must stay 0 (it takes more than two layers = 0.09 m per step, i.e. more than 9 m/s towards the face).
+__device__ __forceinline__ bool exchange_would_miss(int old_layer, int new_layer, const Params &P) {
+    return (P.own_z0 > 0 && old_layer >= P.own_z0 + 4 && new_layer < P.own_z0 + 2) ||
+           (P.own_z1 < P.rz_global && old_layer < P.own_z1 - 4 && new_layer >= P.own_z1 - 2);
 }
 
 // ---- walls + integration, shared by k_integrate_collide and the fused force kernel -------------------

@@ -303,10 +303,10 @@ __device__ __forceinline__ void force_epilogue(const int i, const ForceSum &f, c
         float4 np, nv;
         walls_and_integrate(p, v, a, np, nv, P);
         if (far_movers) {
-            // slab mode: the ghost exchange assumes a particle crosses at most 2 z-layers per step; count offenders
+            // slab mode: count the particles the boundary-only exchange would miss (see exchange_would_miss)
             const int old_layer = __ldg(key + i) / (P.rx * P.xb * P.ry) + P.z_base;
             const int new_layer = cell_coord(np.z, P.hbz, P.h_d, P.rz_global);
-            if (abs(new_layer - old_layer) > 2) atomicAdd(far_movers, 1);
+            if (exchange_would_miss(old_layer, new_layer, P)) atomicAdd(far_movers, 1);
         }
         pos_out[i] = np;
         vel_out[i] = nv;
