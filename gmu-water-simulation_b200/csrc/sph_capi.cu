@@ -422,9 +422,9 @@ int slab_exchange(sph_context *c) {
 int slab_layer_starts(sph_context *c, const int layers[4], int out[4]) {
     Slab &s = *c->slab;
     const size_t rxy = (size_t)c->P.rx * c->P.xb * c->P.ry;  // sort-key entries per z-layer
-    for (int k = 0; k < 4; ++k)
-        CUDA_TRY(c, cudaMemcpyAsync(s.h_pinned + 4 + k, c->g.cell_start + (size_t)layers[k] * rxy, sizeof(int),
-                                    cudaMemcpyDeviceToHost, c->stream));
+    launch_gather4(c->g.cell_start, (size_t)layers[0] * rxy, (size_t)layers[1] * rxy, (size_t)layers[2] * rxy,
+                   (size_t)layers[3] * rxy, s.h_pinned + 4, c->stream);  // zero-copy store into the pinned words
+    c->kernel_launches += 1;
     CUDA_TRY(c, cudaEventRecord(s.ev_ranges, c->stream));
     return SPH_OK;
 }
@@ -454,12 +454,13 @@ int slab_step_sequential(sph_context *c, int n_steps, double *ms) {
     return rc ? rc : t.finish();
 }
 
-// Overlapped slab step.  After the density pass the forces + integration run first on the boundary layers
-// (the four owned layers next to each face: two that become the neighbour's ghosts plus two of slack for
-// particles moving towards the face), then on the interior.  As soon as the boundary is integrated the
-// communication stream packs it and runs the NCCL exchange for the NEXT step, concurrently with the interior
-// kernels; ghosts are neither force-evaluated nor integrated, so the received particles can land directly
-// behind the owned run of A while the interior is still being written.
+// Overlapped slab step.  After the density pass the forces + integration of the boundary layers (the four owned
+// layers next to each face: two that become the neighbour's ghosts plus two of slack for particles moving towards
+// the face) run on the high-priority communication stream, followed there by the pack and the NCCL exchange for
+// the NEXT step; the interior runs concurrently on the compute stream.  Stream priority matters: without it the
+// interior kernel's queued blocks keep every SM slot and the pack only starts when the interior has drained
+// (measured: profiles/r1_timeline_slab_2gpu.txt).  Ghosts are neither force-evaluated nor integrated, so the
+// received particles can land directly behind the owned run of A while the interior is still being written.
 int slab_step_overlapped(sph_context *c, int n_steps, double *ms) {
     Slab &s = *c->slab;
     constexpr int kBoundaryLayers = 4;
@@ -476,19 +477,20 @@ int slab_step_overlapped(sph_context *c, int n_steps, double *ms) {
         int rc = slab_layer_starts(c, layers, nullptr);
         if (rc) return rc;
         enqueue_density(c);  // all local particles: the first ghost layer needs its density too
+        CUDA_TRY(c, cudaEventRecord(s.ev_boundary, c->stream));  // "density done": the boundary work may start
         CUDA_TRY(c, cudaEventSynchronize(s.ev_ranges));  // returns while the density pass is still running
         const int L0 = s.h_pinned[4], L1 = s.h_pinned[5], L2 = s.h_pinned[6], L3 = s.h_pinned[7];
-        auto forces_integrate = [&](int i0, int i1) {  // fused forces + walls + integration on [i0, i1)
-            launch_forces_mask(c->nb, c->dp, c->nb_count, c->g.key_s, c->g.cell_start, c->acc, i0, i1, c->P, c->stream,
+        auto forces_integrate = [&](int i0, int i1, cudaStream_t st) {  // fused forces + walls + integration on [i0, i1)
+            launch_forces_mask(c->nb, c->dp, c->nb_count, c->g.key_s, c->g.cell_start, c->acc, i0, i1, c->P, st,
                                c->pos_s, c->pos_a, c->vel_a, s.d_counters + 4);
             c->kernel_launches += 2;
         };
-        forces_integrate(L0, L1);
-        forces_integrate(L2, L3);
-        CUDA_TRY(c, cudaEventRecord(s.ev_boundary, c->stream));
-        forces_integrate(L1, L2);  // interior: overlaps with the exchange below
-        // ---- exchange for the next step on the communication stream
+        // ---- boundary layers, pack and exchange for the next step: high-priority stream
         CUDA_TRY(c, cudaStreamWaitEvent(s.comm_stream, s.ev_boundary, 0));
+        forces_integrate(L0, L1, s.comm_stream);
+        forces_integrate(L2, L3, s.comm_stream);
+        // ---- interior: compute stream, concurrently (its blocks fill whatever the boundary work leaves free)
+        forces_integrate(L1, L2, c->stream);
         slab_pack_begin(c, s.comm_stream);
         slab_pack_range(c, s.comm_stream, (uint32_t)L0, (uint32_t)(L1 - L0));
         slab_pack_range(c, s.comm_stream, (uint32_t)L2, (uint32_t)(L3 - L2));
@@ -1243,7 +1245,11 @@ int sph_slab_create(const sph_config *cfg, sph_context **out) {
     SLAB_TRY(dalloc(&s->d_counters, (size_t)8));  // [0..3] exchange counts, [4] particles that moved > 2 layers
     SLAB_TRY(cudaMemset(s->d_counters, 0, 8 * sizeof(int)));
     SLAB_TRY(cudaMallocHost(reinterpret_cast<void **>(&s->h_pinned), 8 * sizeof(int)));
-    SLAB_TRY(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+    // highest priority: the boundary kernels, the pack and NCCL must get SM slots ahead of the interior force kernel
+    // that is already filling the device on the compute stream
+    int prio_least = 0, prio_greatest = 0;
+    SLAB_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    SLAB_TRY(cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, prio_greatest));
     SLAB_TRY(cudaEventCreateWithFlags(&s->ev_ranges, cudaEventDisableTiming));
     SLAB_TRY(cudaEventCreateWithFlags(&s->ev_boundary, cudaEventDisableTiming));
     SLAB_TRY(cudaEventCreateWithFlags(&s->ev_counts, cudaEventDisableTiming));

@@ -74,6 +74,7 @@ void launch_aos_to_soa(const ParticleAoS *aos, float4 *pos, float4 *vel, int n, 
 void launch_soa_to_aos(const float4 *pos, const float4 *vel, const float4 *acc, const float4 *dp, const int *key,
                        ParticleAoS *aos_by_id, int id_base, int id_count, int n, const Params &P, cudaStream_t st);
 // slab mode: append the owned particles lying in the 2+2 layers around each face to the send buffers
+void launch_gather4(const int *src, size_t i0, size_t i1, size_t i2, size_t i3, int *dst, cudaStream_t st);
 void launch_slab_pack(const float4 *pos, const float4 *vel, int n, int z_lo_below, int z_hi_from, float4 *down_pos,
                       float4 *down_vel, float4 *up_pos, float4 *up_vel, int *counters, int cap_face, const Params &P,
                       cudaStream_t st);

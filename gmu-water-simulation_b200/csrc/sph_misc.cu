@@ -292,6 +292,15 @@ void launch_slab_pack(const float4 *pos, const float4 *vel, int n, int z_lo_belo
                                                  counters, cap_face, P);
 }
 
+// Four words of one array gathered into (pinned, device-mapped) host memory by a single tiny launch.
+__global__ void k_gather4(const int *__restrict__ src, size_t i0, size_t i1, size_t i2, size_t i3, int *__restrict__ dst) {
+    const size_t idx[4] = {i0, i1, i2, i3};
+    if (threadIdx.x < 4) dst[threadIdx.x] = src[idx[threadIdx.x]];
+}
+void launch_gather4(const int *src, size_t i0, size_t i1, size_t i2, size_t i3, int *dst, cudaStream_t st) {
+    k_gather4<<<1, 32, 0, st>>>(src, i0, i1, i2, i3, dst);
+}
+
 // ================================================================= L2 eviction for benchmarking
 __global__ void __launch_bounds__(256) k_flush_l2(float4 *__restrict__ buf, size_t count) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;

@@ -1,0 +1,57 @@
+"""In-situ timeline of a few slab-mode steps on rank 0 (CUPTI records through torch.profiler), run under torchrun:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/timeline_slab.py [--box 4.56 4.56 36.56] [--steps 3]
+
+Shows what an ncu launch list cannot: which kernels of the overlapped step run concurrently with the exchange and
+where the device idles."""
+import argparse, os, sys
+import torch
+import torch.distributed as dist
+from torch.profiler import ProfilerActivity, profile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import gmu_water_simulation_b200 as gws  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--box", type=float, nargs=3, default=[4.56, 4.56, 36.56])
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--preroll", type=int, default=200)
+ap.add_argument("--no-overlap", action="store_true")
+a = ap.parse_args()
+os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+local = int(os.environ.get("LOCAL_RANK", rank))
+torch.cuda.set_device(local)
+torch.zeros(1, device="cuda")
+ident = [gws.comm_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(ident, src=0)
+sim = gws.Simulator("cuda", tuple(a.box), device=local).enable_slab(rank, world, ident[0]).setup_scene()
+ctx = sim.context()
+if a.no_overlap:
+    ctx.set_option("slab_overlap", 0)
+sim.step_many(a.preroll, timed=False)
+ms = sim.step_many(10)
+dist.barrier()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    t = sim.step_many(a.steps)
+    torch.cuda.synchronize()
+dist.barrier()
+if rank == 0:
+    ev = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
+    print(f"rank 0 of {world}: {ctx.n} local particles, {ms / 10 * 1e3:.1f} us/step before profiling, {t / a.steps * 1e3:.1f} us/step profiled")
+    t0 = ev[0].time_range.start
+    cover_end = t0
+    idle = 0.0
+    for e in ev:
+        s, en = e.time_range.start, e.time_range.end
+        gap = s - cover_end
+        if gap > 0:
+            idle += gap
+        print(f"{e.name[:44]:44s} start {s - t0:9.1f} us  dur {en - s:8.1f} us  {'idle before %.1f us' % gap if gap > 1.0 else ''}")
+        cover_end = max(cover_end, en)
+    span = cover_end - t0
+    print(f"span {span:.1f} us over {a.steps} steps, device idle {idle:.1f} us ({100 * idle / span:.1f} %)")
+dist.barrier()
