@@ -101,6 +101,8 @@ def cuda_lib():
             "sph_upload_particles": (i32, [vp, vp, u32]),
             "sph_append_particles": (i32, [vp, vp, u32]),
             "sph_download_particles": (i32, [vp, vp, u32, P(u32)]),
+            "sph_download_particles_async": (i32, [vp, vp, u32]),
+            "sph_download_wait": (i32, [vp, P(u32)]),
             "sph_particle_count": (i32, [vp, P(u32)]),
             "sph_set_gravity": (i32, [vp, f, f, f]),
             "sph_set_collision_faces": (i32, [vp, vp, u32]),
@@ -158,6 +160,7 @@ def host_lib():
             "gmu_sim_set_mirror_mode": (i32, [vp, i32]),
             "gmu_sim_set_mirror_stride": (i32, [vp, i32]),
             "gmu_sim_sync_host": (i32, [vp]),
+            "gmu_sim_wait_host": (i32, [vp]),
             "gmu_sim_set_gravity": (i32, [vp, f, f, f]),
             "gmu_sim_set_collision_faces": (i32, [vp, vp, i32]),
             "gmu_sim_key": (i32, [vp, i32]),
@@ -297,6 +300,15 @@ class SphContext:
         got = C.c_uint32(0)
         self._ck(self.lib.sph_download_particles(self._h, _ptr(out), out.shape[0], C.byref(got)))
         return out[: got.value]
+
+    def download_async(self, out):
+        """Start an overlapped read-back into `out` (pin it first); contents are defined after download_wait()."""
+        self._ck(self.lib.sph_download_particles_async(self._h, _ptr(out), out.shape[0]))
+
+    def download_wait(self):
+        got = C.c_uint32(0)
+        self._ck(self.lib.sph_download_wait(self._h, C.byref(got)))
+        return got.value
 
     def pin(self, arr):
         self._ck(self.lib.sph_pin_host_buffer(self._h, _ptr(arr), arr.nbytes))
@@ -490,6 +502,9 @@ class Simulator:
 
     def sync_host(self):
         self._ck(self.lib.gmu_sim_sync_host(self._h))
+
+    def wait_host(self):
+        self._ck(self.lib.gmu_sim_wait_host(self._h))
 
     def set_gravity(self, g):
         self._ck(self.lib.gmu_sim_set_gravity(self._h, float(g[0]), float(g[1]), float(g[2])))

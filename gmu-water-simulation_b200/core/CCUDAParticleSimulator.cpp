@@ -124,8 +124,14 @@ void CCUDAParticleSimulator::step() {
                                                m_deviceCount), "step upload");
         }
         CBaseParticleSimulator::step();
-        if (m_mirrorMode == RoundTrip || (m_mirrorMode == Download && (getTotalIteration() + 1) % (unsigned long)m_mirrorStride == 0))
+        const bool refresh = (getTotalIteration() + 1) % (unsigned long)m_mirrorStride == 0;
+        if (m_mirrorMode == RoundTrip || (m_mirrorMode == Download && refresh)) {
             syncHostMirror();
+        } else if (m_mirrorMode == AsyncDownload && refresh) {
+            // snapshot now (device-side, ~15 us per million particles), PCIe copy overlapped with the next steps
+            m_cuda->check(sph_download_particles_async(m_cuda->ctx(), reinterpret_cast<sph_particle *>(m_clParticles.data()),
+                                                       (uint32_t)m_clParticles.size()), "async mirror");
+        }
     } catch (CUDAException &exc) {
         emitErrorOccured(exc.what());
         stop();
@@ -141,6 +147,10 @@ void CCUDAParticleSimulator::stepMany(int steps, double *deviceMs) {
     }
     m_cuda->check(sph_step(m_cuda->ctx(), steps, deviceMs), "stepMany");
     addIterations((unsigned long)steps);
+}
+
+void CCUDAParticleSimulator::waitHostMirror() {
+    if (m_cuda) m_cuda->check(sph_download_wait(m_cuda->ctx(), nullptr), "waitHostMirror");
 }
 
 void CCUDAParticleSimulator::syncHostMirror() {

@@ -19,7 +19,10 @@ public:
     //   RoundTrip — upload before and read back after every step: the reference OpenCL path's
     //               semantics, where the host vector is canonical (src/CGPUParticleSimulator.cpp:61,
     //               src/CGPUBaseParticleSimulator.cpp:84)
-    enum MirrorMode { Resident = 0, Download = 1, RoundTrip = 2 };
+    //   AsyncDownload — like Download, but the read-back runs on a copy stream while the next steps compute
+    //               (sph_download_particles_async); waitHostMirror() completes the snapshot in flight, so the mirror
+    //               shows the state of the last refresh step without ever stalling the simulation on PCIe
+    enum MirrorMode { Resident = 0, Download = 1, RoundTrip = 2, AsyncDownload = 3 };
 
     explicit CCUDAParticleSimulator(CScene *scene, float boxSize, int device = 0, SimulationScenario scenario = DAM_BREAK,
                                     QObject *parent = nullptr);
@@ -34,7 +37,8 @@ public:
 
     // extensions used by the headless bench and the tests
     void stepMany(int steps, double *deviceMs = nullptr);  // fused steps on the device (dam break: one CUDA graph)
-    void syncHostMirror();                                 // device -> m_clParticles (indexed by id)
+    void syncHostMirror();                                 // device -> m_clParticles (indexed by id), blocking, current state
+    void waitHostMirror();                                 // AsyncDownload: finish the read-back in flight (no-op otherwise)
     void setMirrorMode(MirrorMode m) { m_mirrorMode = m; }
     // viewer bridge: in Download mode refresh the host mirror only every `stride`-th step (a 60 Hz viewer does not
     // need 1500 read-backs per second); 1 = every step like the reference's OpenCL path

@@ -170,7 +170,14 @@ uint64_t gmu_sim_particle_count(gmu_sim *s) { return H(s)->sim->getParticlesCoun
 uint64_t gmu_sim_max_particle_count(gmu_sim *s) { return H(s)->sim->getMaxParticlesCount(); }
 uint64_t gmu_sim_iteration(gmu_sim *s) { return H(s)->sim->getTotalIteration(); }
 
+int gmu_sim_wait_host(gmu_sim *s) {
+    return guarded([&] {
+        if (H(s)->cuda) H(s)->cuda->waitHostMirror();
+    });
+}
+
 const sph_particle *gmu_sim_host_particles(gmu_sim *s) {
+    if (H(s)->cuda) guarded([&] { H(s)->cuda->waitHostMirror(); });  // never hand out a half-copied snapshot
     return reinterpret_cast<const sph_particle *>(H(s)->sim->getHostParticles().data());
 }
 

@@ -59,6 +59,11 @@ struct sph_context {
     std::string err;
     void *pinned_ptr = nullptr;
     float4 *d_mesh_planes = nullptr;  // sph_set_collision_faces
+    // asynchronous read-back (sph_download_particles_async): snapshot on `stream`, PCIe copy on `copy_stream`
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_copy = nullptr;
+    bool copy_pending = false;
+    uint32_t copy_n = 0;
     // bench hygiene: evict L2 between timed steps (option "flush_l2") and time each step separately
     int opt_flush_l2 = 0;
     float4 *d_flush = nullptr;
@@ -584,6 +589,12 @@ int sph_destroy(sph_context *c) {
         if (p) cudaFree(p);
     if (c->d_flush) cudaFree(c->d_flush);
     if (c->d_mesh_planes) cudaFree(c->d_mesh_planes);
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamDestroy(c->copy_stream);
+    }
+    if (c->ev_snap) cudaEventDestroy(c->ev_snap);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     slab_release(c);
     for (cudaEvent_t e : c->step_events) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -686,7 +697,17 @@ int sph_create(const sph_config *cfg, sph_context **out) {
 const char *sph_last_error(const sph_context *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
 
 // ---------------------------------------------------------------- state
+// d_stage is shared by uploads and read-backs: an asynchronous copy still in flight has to drain first
+static int drain_async_download(sph_context *c) {
+    if (c->copy_pending) {
+        CUDA_TRY(c, cudaEventSynchronize(c->ev_copy));
+        c->copy_pending = false;
+    }
+    return SPH_OK;
+}
+
 static int upload_range(sph_context *c, const sph_particle *aos, uint32_t first, uint32_t count) {
+    if (int rc = drain_async_download(c)) return rc;
     for (uint32_t done = 0; done < count;) {
         const uint32_t chunk = (uint32_t)std::min<size_t>(count - done, c->stage_cap);
         CUDA_TRY(c, cudaMemcpyAsync(c->d_stage, aos + done, (size_t)chunk * sizeof(sph_particle), cudaMemcpyHostToDevice,
@@ -732,6 +753,7 @@ int sph_download_particles(sph_context *c, sph_particle *aos, uint32_t capacity,
     REQUIRE(c, aos && capacity >= c->n, SPH_ERR_ARGUMENT, "sph_download_particles: buffer too small");
     REQUIRE(c, !c->slab, SPH_ERR_STATE, "sph_download_particles: indexed by global id - not available in slab mode (use sph_download_owned)");
     CUDA_TRY(c, cudaSetDevice(c->device));
+    if (int rc = drain_async_download(c)) return rc;
     const bool aux = aux_aligned(c);
     for (uint32_t base = 0; base < c->n;) {
         const uint32_t chunk = (uint32_t)std::min<size_t>(c->n - base, c->stage_cap);
@@ -746,6 +768,43 @@ int sph_download_particles(sph_context *c, sph_particle *aos, uint32_t capacity,
     }
     if (n_out) *n_out = c->n;
     return check_launch(c, "soa_to_aos");
+}
+
+int sph_download_particles_async(sph_context *c, sph_particle *aos, uint32_t capacity) {
+    REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    REQUIRE(c, aos && capacity >= c->n, SPH_ERR_ARGUMENT, "sph_download_particles_async: buffer too small");
+    REQUIRE(c, !c->slab, SPH_ERR_STATE, "sph_download_particles_async: not available in slab mode (use sph_download_owned)");
+    REQUIRE(c, c->n <= c->stage_cap, SPH_ERR_ARGUMENT, "sph_download_particles_async: more particles than the staging buffer holds; use sph_download_particles");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (!c->copy_stream) {
+        CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+    }
+    // the previous copy must have left the staging buffer before the snapshot kernel overwrites it (device-side wait)
+    if (c->copy_pending) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+    c->copy_n = c->n;
+    if (c->n > 0) {
+        const bool aux = aux_aligned(c);
+        launch_soa_to_aos(view_pos(c), view_vel(c), aux ? c->acc : nullptr, aux ? c->dp : nullptr,
+                          (aux && c->grid_valid) ? c->g.key_s : nullptr, c->d_stage, 0, (int)c->n, (int)c->n, c->P, c->stream);
+        c->kernel_launches += 1;
+    }
+    CUDA_TRY(c, cudaEventRecord(c->ev_snap, c->stream));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_snap, 0));
+    if (c->n > 0)
+        CUDA_TRY(c, cudaMemcpyAsync(aos, c->d_stage, (size_t)c->n * sizeof(sph_particle), cudaMemcpyDeviceToHost, c->copy_stream));
+    CUDA_TRY(c, cudaEventRecord(c->ev_copy, c->copy_stream));
+    c->copy_pending = true;
+    return check_launch(c, "soa_to_aos (async)");
+}
+
+int sph_download_wait(sph_context *c, uint32_t *n_out) {
+    REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (int rc = drain_async_download(c)) return rc;
+    if (n_out) *n_out = c->copy_n;
+    return SPH_OK;
 }
 
 int sph_particle_count(const sph_context *c, uint32_t *n_out) {

@@ -107,6 +107,14 @@ int sph_upload_particles(sph_context *ctx, const sph_particle *aos, uint32_t n);
 int sph_append_particles(sph_context *ctx, const sph_particle *aos, uint32_t n_new);
 /* Read back on demand into aos[id] (the host mirror is indexed by id); capacity in records. */
 int sph_download_particles(sph_context *ctx, sph_particle *aos, uint32_t capacity, uint32_t *n_out);
+/* Viewer bridge (≙ the read-back + updatePosition/updateVelocity loop, src/CGPUBaseParticleSimulator.cpp:84-91, which
+ * was the reference's dominant cost): the state is snapshotted into device staging on the compute stream (about 15 us
+ * per million particles) and copied to aos[id] on a separate copy stream while later steps run.  aos should be
+ * page-locked (sph_pin_host_buffer); its contents are defined once sph_download_wait returns.  One download can be
+ * in flight - starting another first waits (on the device, not the host) for the previous copy.  Needs the particle
+ * count to fit the staging buffer (4 Mi records), else SPH_ERR_ARGUMENT: use the blocking call. */
+int sph_download_particles_async(sph_context *ctx, sph_particle *aos, uint32_t capacity);
+int sph_download_wait(sph_context *ctx, uint32_t *n_out); /* no-op when nothing is in flight; n_out may be NULL */
 int sph_particle_count(const sph_context *ctx, uint32_t *n_out);
 /* ≙ CGPUBaseParticleSimulator::setGravityVector, src/CGPUBaseParticleSimulator.cpp:11-15 */
 int sph_set_gravity(sph_context *ctx, float gx, float gy, float gz);

@@ -31,9 +31,10 @@ int gmu_sim_setup_scene(gmu_sim *s);                               /* setupScene
 int gmu_sim_step(gmu_sim *s, int n);                               /* n timer ticks: doWork() = step() + counters */
 int gmu_sim_step_many(gmu_sim *s, int n, double *device_ms);       /* fused device steps (extension) */
 int gmu_sim_emit(gmu_sim *s, int n_steps);                         /* scene_only: run the emitter n steps */
-int gmu_sim_set_mirror_mode(gmu_sim *s, int mode);                 /* 0 resident, 1 download, 2 round trip per step */
+int gmu_sim_set_mirror_mode(gmu_sim *s, int mode);                 /* 0 resident, 1 download, 2 round trip per step, 3 asynchronous download */
 int gmu_sim_set_mirror_stride(gmu_sim *s, int stride);              /* download mode: refresh every stride-th step */
-int gmu_sim_sync_host(gmu_sim *s);                                 /* device -> host mirror */
+int gmu_sim_sync_host(gmu_sim *s);                                 /* device -> host mirror, blocking, current state */
+int gmu_sim_wait_host(gmu_sim *s);                                 /* mode 3: complete the read-back in flight */
 int gmu_sim_set_gravity(gmu_sim *s, float gx, float gy, float gz); /* setGravityVector */
 int gmu_sim_key(gmu_sim *s, int qt_key);                           /* onKeyPressed */
 /* collision mesh for CCollisionGeometry::inverseBounce: n faces x 12 floats (normal, v0, v1, v2); 0 clears it */

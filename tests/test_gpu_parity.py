@@ -510,3 +510,44 @@ def test_full_size_parity_against_oracle_1m(gws):
     o.integrate()
     assert np.all(np.abs(rec["position"][:, :3] - o.pos) <= tol)
     assert ctx.counter("overflow_particles") == 0
+
+
+def test_async_download_is_a_consistent_snapshot(gws):
+    """Viewer bridge (row f2): the overlapped read-back delivers exactly the state at the moment it was requested,
+    while later steps are already running; a second request queues behind the first on the device."""
+    box = 0.9
+    o = state_after(box, 3)
+    ctx = make_ctx(gws, box, o.pos, o.vel)
+    ctx.step(2)
+    ref = ctx.download().copy()                      # blocking read-back of the same moment
+    out = np.zeros(o.n, dtype=gws.PARTICLE_DTYPE)
+    ctx.pin(out)
+    ctx.download_async(out)
+    ctx.step(5, timed=False)                         # keeps the device busy while the copy is in flight
+    assert ctx.download_wait() == o.n
+    assert out.tobytes() == ref.tobytes()
+    ref2 = None
+    ctx.download_async(out)                          # state after 7 steps
+    ctx.step(1, timed=False)
+    ctx.download_async(out)                          # state after 8 steps: waits for the first copy on the device
+    ctx.download_wait()
+    ref2 = ctx.download()
+    assert out.tobytes() == ref2.tobytes()
+    assert ctx.download_wait() == o.n                # nothing in flight: returns immediately
+    ctx.close()
+
+
+def test_simulator_async_mirror_mode(gws):
+    box = 0.4
+    o = Oracle(box).setup_scene()
+    sim = gws.Simulator("cuda", box).setup_scene()
+    sim.set_mirror_mode(3)                           # AsyncDownload
+    sim.set_mirror_stride(2)
+    sim.step(4); o.step(4)                           # refreshes requested after steps 2 and 4
+    hp = sim.host_particles()                        # completes the copy in flight
+    assert np.abs(hp["position"][:, :3] - o.pos).max() <= 1e-4 * 0.0457
+    sim.step(1); o.step(1)                           # step 5: no refresh, the mirror still shows step 4
+    assert np.abs(sim.host_particles()["position"][:, :3] - o.pos).max() > 0
+    sim.sync_host()                                  # blocking: current state
+    assert np.abs(sim.host_particles()["position"][:, :3] - o.pos).max() <= 1e-4 * 0.0457
+    sim.close()
