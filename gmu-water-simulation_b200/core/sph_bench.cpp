@@ -3,7 +3,7 @@
 // reference's own per-phase split (sProfilingEvent).  No Qt, no viewer.
 //
 //   sph_bench [--scenario dam_break|fountain] [--box B | --box3 X Y Z] [--steps K] [--warmup W]
-//             [--device D] [--brute] [--phases] [--mirror 0|1|2] [--nozzles M] [--csv DIR]
+//             [--device D] [--brute] [--phases] [--mirror 0|1|2|3] [--mirror-stride K] [--nozzles M] [--csv DIR]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -17,7 +17,7 @@
 int main(int argc, char **argv) {
     std::string scenario = "dam_break", csv;
     float box[3] = {0.9f, 0.9f, 0.9f};
-    int steps = 100, warmup = 10, device = 0, mirror = 0, nozzles = 1;
+    int steps = 100, warmup = 10, device = 0, mirror = 0, mirror_stride = 1, nozzles = 1;
     bool brute = false, phases = false;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
@@ -31,7 +31,8 @@ int main(int argc, char **argv) {
         else if (a == "--steps") steps = std::atoi(next("--steps"));
         else if (a == "--warmup") warmup = std::atoi(next("--warmup"));
         else if (a == "--device") device = std::atoi(next("--device"));
-        else if (a == "--mirror") mirror = std::atoi(next("--mirror"));
+        else if (a == "--mirror") mirror = std::atoi(next("--mirror"));  // 0 resident, 1 download, 2 round trip, 3 async download
+        else if (a == "--mirror-stride") mirror_stride = std::atoi(next("--mirror-stride"));
         else if (a == "--nozzles") nozzles = std::atoi(next("--nozzles"));
         else if (a == "--csv") csv = next("--csv");
         else if (a == "--brute") brute = true;
@@ -46,6 +47,7 @@ int main(int argc, char **argv) {
         auto *sim = static_cast<CCUDAParticleSimulator *>(base.get());
         sim->setEmissionMultiplier(nozzles);
         sim->setMirrorMode((CCUDAParticleSimulator::MirrorMode)mirror);
+        sim->setMirrorStride(mirror_stride);
         sim->onErrorOccured([](const char *what) { std::fprintf(stderr, "error: %s\n", what); std::exit(1); });
         sim->setupScene();
         std::fprintf(stderr, "device: %s\nparticles: %lu (max %lu)\n", sim->getSelectedDevice().c_str(), sim->getParticlesCount(),
@@ -69,6 +71,7 @@ int main(int argc, char **argv) {
             sim->stepMany(steps);
             particle_steps = (double)steps * (double)sim->getParticlesCount();
         }
+        sim->waitHostMirror();  // mode 3: the last overlapped read-back belongs to the timed region
         sph_synchronize(sim->context());
         const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         double ph[5] = {0, 0, 0, 0, 0};
