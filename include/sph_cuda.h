@@ -101,7 +101,9 @@ int sph_destroy(sph_context *ctx);
 const char *sph_last_error(const sph_context *ctx); /* ctx may be NULL: error of the last failed create/enumeration */
 
 /* ---- state (≙ enqueueWrite/enqueueRead, include/CLWrapper.h:66-67) ---- */
-/* Replace the device state with n particles from the 80-byte AoS host mirror (m_clParticles). */
+/* Replace the device state with n particles from the 80-byte AoS host mirror (m_clParticles).  From a page-locked
+ * buffer (sph_pin_host_buffer) the copy is asynchronous on the context's stream: leave the records alone until
+ * the next synchronising call (a timed phase, sph_download_particles, sph_synchronize). */
 int sph_upload_particles(sph_context *ctx, const sph_particle *aos, uint32_t n);
 /* Fountain emission (src/CBaseParticleSimulator.cpp:187-210): append n_new particles. */
 int sph_append_particles(sph_context *ctx, const sph_particle *aos, uint32_t n_new);
