@@ -109,17 +109,26 @@ def run_reference(args):
     from oracle_binding import Oracle, build_oracle
 
     build_oracle()
-    # bounded sample: the largest dam-break scene whose K+W steps fit in ~150 s of single-thread CPU time
-    budget = 150.0 / max(args.steps + args.warmup, 1)
-    per_particle_step = 3.3e-6
-    name = "dam_break_16K"
-    for cand in ("dam_break_1M", "dam_break_250K", "dam_break_32K", "dam_break_16K"):
-        if WORKLOADS[cand][1] * per_particle_step <= budget:
-            name = cand
-            break
-    if args.reference_sample:
-        name = args.reference_sample
-    box, n = WORKLOADS[name]
+    # bounded sample of our arm's workload whose K+W steps fit in about two minutes of single-thread CPU time: N=1 the largest
+    # dam-break cube that fits, N>1 a slice of the 64M tank (same cross-section and lattice, shorter in z)
+    budget = 110.0 / max(args.steps + args.warmup, 1)
+    per_particle_step = 4.0e-6
+    if args.gpus > 1:
+        workload, scaling = "tank_64M", "strong"
+        frac = min(1.0, budget / per_particle_step / 64.0e6)
+        cells_z = max(4, int(TANK_BOX[2] * frac / 0.0457))
+        box = (TANK_BOX[0], TANK_BOX[1], cells_z * 0.0457)
+        name = f"tank slice {box[0]} x {box[1]} x {box[2]:.4f}"
+    else:
+        workload, scaling = "dam_break_1M", "weak"
+        name = "dam_break_16K"
+        for cand in ("dam_break_1M", "dam_break_250K", "dam_break_32K", "dam_break_16K"):
+            if WORKLOADS[cand][1] * per_particle_step <= budget:
+                name = cand
+                break
+        if args.reference_sample:
+            name = args.reference_sample
+        box, _ = WORKLOADS[name]
     o = Oracle(box).setup_scene()
     o.step(args.warmup)
     t0 = time.perf_counter()
@@ -128,12 +137,13 @@ def run_reference(args):
     value = o.n * args.steps / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "dam_break_1M", "sample": name, "particles": o.n,
+        "config": {"workload": workload, "sample": name, "particles": o.n,
                    "note": "CPU oracle = single-threaded port of the reference's CCPUParticleSimulator (reference needs Qt5+OpenCL, unbuildable here)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"{name}: {o.n} particles x {args.steps} steps from the initial lattice (after {args.warmup} warm-up steps)"},
+                         "sample": f"{name}: {o.n} particles x {args.steps} steps from the initial lattice (after {args.warmup} warm-up steps); "
+                                   "the lattice has fewer neighbours per particle than the pre-rolled state our arm times, so this favours the CPU"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "phase_ms": dict(zip(["grid", "density", "forces", "collisions", "integrate"], (phase / args.steps).tolist())),
     }
