@@ -62,6 +62,39 @@ def test_isolated_particle():
     assert a[0] == 0 and a[2] == 0 and abs(a[1] - (-9.80665)) < 2e-6
 
 
+def test_two_particle_closed_form():
+    """Pair of particles: density, pressure and both force terms against the formulas of the reference evaluated in
+    fp64 (src/CCPUParticleSimulator.cpp:9-30 kernels, :122-134 density/pressure, :174-195 forces).  Also pins the
+    sign conventions: a compressed pair (p > 0 needs rho > rho0; here p < 0) attracts, viscosity pulls velocities together."""
+    import math
+    h, m, k, rho0, mu, g = float(np.float32(0.0457)), 0.02, 3.0, float(np.float32(998.29)), 3.5, -9.80665
+    poly6 = 315.0 / (64.0 * math.pi * h ** 9)
+    spiky = -45.0 / (math.pi * h ** 6)
+    visc = 45.0 / (math.pi * h ** 6)
+    xi, xj = np.array([0.0, 0.0, 0.0]), np.array([0.02, 0.01, -0.005])
+    vi, vj = np.array([0.3, -0.2, 0.1]), np.array([-0.1, 0.4, 0.25])
+    o = Oracle(0.9)
+    o.set_state(np.array([xi, xj], dtype=np.float32), np.array([vi, vj], dtype=np.float32))
+    o.update_grid(); o.update_density_pressure(); o.update_forces()
+    xi, xj = np.float32(xi).astype(np.float64), np.float32(xj).astype(np.float64)
+    vi, vj = np.float32(vi).astype(np.float64), np.float32(vj).astype(np.float64)
+    d = xi - xj
+    r2 = float(d @ d)
+    r = math.sqrt(r2)
+    assert r < h
+    rho = m * poly6 * ((h * h) ** 3 + (h * h - r2) ** 3)     # self + the one neighbour, identical for both
+    p = k * (rho - rho0)
+    assert np.allclose(o.density, rho, rtol=2e-6) and np.allclose(o.pressure, p, rtol=1e-5)
+    grad = spiky * (h - r) ** 2 * d / r                        # WspikyGradient(x_i - x_j)
+    f_p = (p / rho ** 2 + p / rho ** 2) * grad
+    f_v = visc * (h - r) * (vj - vi) / rho                     # WviscosityLaplacian * (v_j - v_i) / rho_j
+    a_i = ((-m * rho) * f_p + (mu * m) * f_v + np.array([0.0, g, 0.0]) * rho) / rho
+    a_j = ((-m * rho) * (-f_p) + (mu * m) * (-f_v) + np.array([0.0, g, 0.0]) * rho) / rho
+    assert np.allclose(o.acc_sph[0], a_i, rtol=2e-5, atol=1e-6) and np.allclose(o.acc_sph[1], a_j, rtol=2e-5, atol=1e-6)
+    assert p < 0 and np.dot(a_i - np.array([0.0, g, 0.0]) - (mu * m) * f_v / rho, xj - xi) > 0   # negative pressure attracts
+    assert np.dot((mu * m) * f_v, vj - vi) > 0                                                  # viscosity damps the relative motion
+
+
 def test_lattice_step0_neighbour_statistics():
     # probe values recorded in SURVEY.md §8c for N=1620 (box 0.4)
     o = Oracle(0.4).setup_scene()
