@@ -149,6 +149,14 @@ void CCUDAParticleSimulator::stepMany(int steps, double *deviceMs) {
     addIterations((unsigned long)steps);
 }
 
+void CCUDAParticleSimulator::setMirrorMode(MirrorMode m) {
+    // RoundTrip makes the host vector canonical (it is uploaded before every step, like the reference's OpenCL
+    // path).  Entering it after resident steps with a stale mirror would silently rewind the simulation to whatever
+    // the mirror last held, so the mirror is brought up to date first.
+    if (m == RoundTrip && m_mirrorMode != RoundTrip && m_cuda && !m_slab) syncHostMirror();
+    m_mirrorMode = m;
+}
+
 void CCUDAParticleSimulator::waitHostMirror() {
     if (m_cuda) m_cuda->check(sph_download_wait(m_cuda->ctx(), nullptr), "waitHostMirror");
 }

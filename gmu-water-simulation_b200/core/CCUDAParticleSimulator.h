@@ -39,7 +39,7 @@ public:
     void stepMany(int steps, double *deviceMs = nullptr);  // fused steps on the device (dam break: one CUDA graph)
     void syncHostMirror();                                 // device -> m_clParticles (indexed by id), blocking, current state
     void waitHostMirror();                                 // AsyncDownload: finish the read-back in flight (no-op otherwise)
-    void setMirrorMode(MirrorMode m) { m_mirrorMode = m; }
+    void setMirrorMode(MirrorMode m);
     // viewer bridge: in Download mode refresh the host mirror only every `stride`-th step (a 60 Hz viewer does not
     // need 1500 read-backs per second); 1 = every step like the reference's OpenCL path
     void setMirrorStride(int stride) { m_mirrorStride = stride < 1 ? 1 : stride; }

@@ -551,3 +551,19 @@ def test_simulator_async_mirror_mode(gws):
     sim.sync_host()                                  # blocking: current state
     assert np.abs(sim.host_particles()["position"][:, :3] - o.pos).max() <= 1e-4 * 0.0457
     sim.close()
+
+
+def test_round_trip_mode_continues_from_the_device_state(gws):
+    """Switching to RoundTrip after resident steps must not rewind the simulation to the stale host mirror."""
+    box = 0.4
+    o = Oracle(box).setup_scene()
+    sim = gws.Simulator("cuda", box).setup_scene()
+    sim.step_many(12)                                # resident: the host mirror still holds the initial lattice
+    sim.set_mirror_mode(2)                           # brings the mirror up to date before it becomes canonical
+    sim.step(3)
+    o.step(15)
+    hp = sim.host_particles()
+    # a rewind would show up as centimetres (12 steps of free fall); chaos after 15 steps is micrometres
+    assert np.abs(hp["position"][:, :3] - o.pos).max() <= 1e-3
+    assert sim.iteration == 15
+    sim.close()
