@@ -106,3 +106,18 @@ def test_export_logs_layout(gws, tmp_path):
     detail = (tmp_path / "Dam_break_0.4_detail.csv").read_text().strip().splitlines()
     assert total[0] == "CUDA Grid" and len(total) == 4
     assert [r.split(";")[1] for r in detail] == ["Grid", "Density + pressure", "Forces", "Collisions", "Integrate"]
+
+
+@pytest.mark.parametrize("header", ["sph_cuda.h", "sph_host.h"])
+def test_public_headers_are_plain_c(header, tmp_path):
+    """The boundary is a C ABI: both headers must compile as C99 on their own (no C++, no CUDA or torch types)."""
+    import shutil
+    import subprocess
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "t.c"
+    src.write_text(f'#include "{header}"\nint main(void) {{ return 0; }}\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.check_call([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", str(src)])
