@@ -121,3 +121,28 @@ def test_public_headers_are_plain_c(header, tmp_path):
     src.write_text(f'#include "{header}"\nint main(void) {{ return 0; }}\n')
     inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
     subprocess.check_call([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", str(src)])
+
+
+def test_plain_c_example_links_and_fails_loudly_without_a_device(gws, tmp_path):
+    """examples/minimal_step.c is the ABI used from C.  It must link against libsph_cuda.so alone; without a GPU it
+    reports the CUDA error and exits 1 (no CPU fallback), with one it steps 16 000 particles."""
+    import shutil
+    import subprocess
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(gws.binding._CUDA_SO)
+    exe = str(tmp_path / "minimal_step")
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "minimal_step.c"),
+                           "-L", libdir, "-lsph_cuda", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe])
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    try:
+        has_gpu = gws.device_count() > 0
+    except gws.SphError:
+        has_gpu = False
+    if has_gpu:
+        assert run.returncode == 0 and "16000 particles" in run.stdout, run.stderr
+    else:
+        assert run.returncode == 1 and "CUDA::" in run.stderr
