@@ -13,8 +13,10 @@ the whole scene.  N=1 workload: dam break, box 3.62 -> 1,011,240 particles (BASE
            back — the host<->device traffic of the reference's OpenCL path;
 * roofline / cpu_baseline / clocks / gpu_launches as the driver contract asks.
 
---impl reference times the CPU oracle (a faithful single-threaded restatement of the reference's
-CCPUParticleSimulator; the reference itself needs Qt5+OpenCL and cannot be built) on the host.
+--impl reference times the reference's own CPU implementation on the host: oracle/_ref/libsph_ref.so, the
+reference's CCPUParticleSimulator sources compiled unmodified against stand-in Qt headers ("kind": "reference");
+only where that file is missing (a checkout that never saw /root/reference) the bit-identical oracle port
+("kind": "port").  Single-threaded, because the reference's CPU path is.
 """
 import argparse
 import json
@@ -102,13 +104,27 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference(args):
-    """CPU arm: the oracle (port of CCPUParticleSimulator) on the host cores; rank 0 only."""
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
+def cpu_arm(box, scenario=0):
+    """The CPU implementation to time: the reference's own code (oracle/_ref) when built, else the oracle port
+    (bit-identical to it, tests/test_ref_pins_oracle.py).  Returns (simulator, kind, description)."""
+    import ref_binding
+
+    cube = len(set(float(b) for b in box)) == 1
+    if cube and ref_binding.available():
+        return (ref_binding.Reference(box[0], scenario).setup_scene(), "reference",
+                "oracle/_ref: the reference's CCPUParticleSimulator sources compiled unmodified (Qt stand-ins), 1 thread")
     from oracle_binding import Oracle, build_oracle
 
     build_oracle()
+    why = "the reference's ctor only takes a cube" if not cube else "oracle/_ref is not built here"
+    return (Oracle(box, scenario).setup_scene(), "port",
+            f"oracle port of CCPUParticleSimulator, bit-identical to oracle/_ref on the test scenes ({why}), 1 thread")
+
+
+def run_reference(args):
+    """CPU arm: the reference's own CPU simulator on the host cores (single-threaded like the reference); rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
     # bounded sample of our arm's workload whose K+W steps fit in about two minutes of single-thread CPU time: N=1 the largest
     # dam-break cube that fits, N>1 a slice of the 64M tank (same cross-section and lattice, shorter in z)
     budget = 110.0 / max(args.steps + args.warmup, 1)
@@ -129,41 +145,44 @@ def run_reference(args):
         if args.reference_sample:
             name = args.reference_sample
         box, _ = WORKLOADS[name]
-    o = Oracle(box).setup_scene()
+    o, kind, what = cpu_arm(box)
     o.step(args.warmup)
     t0 = time.perf_counter()
-    phase = o.step(args.steps)
+    o.step(args.steps)
     sec = time.perf_counter() - t0
     value = o.n * args.steps / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "sample": name, "particles": o.n,
-                   "note": "CPU oracle = single-threaded port of the reference's CCPUParticleSimulator (reference needs Qt5+OpenCL, unbuildable here)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+        "config": {"workload": workload, "sample": name, "particles": o.n, "note": what},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
                          "sample": f"{name}: {o.n} particles x {args.steps} steps from the initial lattice (after {args.warmup} warm-up steps); "
                                    "the lattice has fewer neighbours per particle than the pre-rolled state our arm times, so this favours the CPU"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "phase_ms": dict(zip(["grid", "density", "forces", "collisions", "integrate"], (phase / args.steps).tolist())),
     }
     print(json.dumps(line), flush=True)
 
 
 def cpu_baseline_sample(pos, vel, box, seconds=12.0):
-    """Oracle timed on a bounded sample of the SAME state the GPU is benchmarked on."""
+    """The CPU implementation timed on a bounded sample of the SAME state the GPU is benchmarked on."""
     from oracle_binding import Oracle
 
-    o = Oracle(box).set_state(pos, vel)
-    o.step(1)  # first step also pays the initial grid fill from cell 0
+    o, kind, what = cpu_arm(box)
+    if kind == "reference":
+        o.set_state(pos, vel)  # same particle count as the scene (dam break): positions / velocities overwritten
+    else:
+        o = Oracle(box).set_state(pos, vel)
+    o.step(1)  # the first step also pays for moving every particle to its cell
     n_steps = max(1, int(seconds / (o.n * 3.3e-6)))
     t0 = time.perf_counter()
     o.step(n_steps)
     sec = time.perf_counter() - t0
-    out = {"value": o.n * n_steps / sec, "unit": UNIT, "cores": 1, "kind": "port",
-           "sample": f"{o.n} particles (the benchmarked state) x {n_steps} step(s), oracle single-threaded like the reference CPU path"}
-    # extra, clearly NOT the reference's behaviour (its CPU path has no threading): the same oracle with its density and
+    out = {"value": o.n * n_steps / sec, "unit": UNIT, "cores": 1, "kind": kind,
+           "sample": f"{o.n} particles (the benchmarked state) x {n_steps} step(s); {what}"}
+    # extra, clearly NOT the reference's behaviour (its CPU path has no threading): the oracle port with its density and
     # force loops spread over all host cores (bit-identical results)
+    o = Oracle(box).set_state(pos, vel)
     threads = o.set_threads(0)
     if threads > 1:
         o.step(1)
@@ -171,7 +190,7 @@ def cpu_baseline_sample(pos, vel, box, seconds=12.0):
         o.step(n_steps)
         sec = time.perf_counter() - t0
         out["all_cores_variant"] = {"value": o.n * n_steps / sec, "unit": UNIT, "cores": threads,
-                                    "note": "not reference behaviour: oracle density/force loops on all host cores"}
+                                    "note": "not reference behaviour: oracle port with density/force loops on all host cores"}
     return out
 
 

@@ -1,8 +1,9 @@
 /*
  * sph_oracle.cpp — CPU ORACLE: restatement of the reference's CCPUParticleSimulator.
  *
- * TEST INFRASTRUCTURE ONLY (see sph_oracle.h).  PARITY UNPINNED by reference tests (it has none);
- * pinned by known answers + an independent numpy restatement in tests/.
+ * TEST INFRASTRUCTURE ONLY (see sph_oracle.h).  PARITY PINNED: this file must match, bit for bit, the
+ * reference's own unmodified sources compiled into oracle/_ref (tests/test_ref_pins_oracle.py) and the
+ * vectors that build produced (tests/golden/ref_*.npz).
  *
  * Build: g++ -O2 -ffp-contract=off (no -ffast-math, no -march FMA) so that every fp32/fp64
  * operation rounds exactly as the reference's x86-64 build does.
@@ -234,6 +235,15 @@ void oracle_set_state(OracleSim *s, int64_t n, const float *pos, const float *ve
     for (int64_t i = 0; i < n; ++i)
         oracle_add_particle(s, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]);
     if (s->max_count < n) s->max_count = n;
+}
+
+int oracle_overwrite_state(OracleSim *s, int64_t n, const float *pos, const float *vel) {
+    if (n != s->n()) return -1;
+    for (int64_t i = 0; i < n; ++i) {
+        s->pos[i] = V3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+        s->vel[i] = V3(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]);
+    }
+    return 0;
 }
 
 void oracle_set_gravity(OracleSim *s, float gx, float gy, float gz) { s->gravity = V3(gx, gy, gz); }
@@ -512,6 +522,15 @@ void oracle_get_cells(const OracleSim *s, int32_t *cell_start, int32_t *ids) {
         std::vector<int32_t> m(s->cells[c]);
         std::sort(m.begin(), m.end());
         for (int32_t id : m) ids[run++] = id;
+    }
+    cell_start[s->cells.size()] = run;
+}
+
+void oracle_get_cells_raw(const OracleSim *s, int32_t *cell_start, int32_t *ids) {
+    int32_t run = 0;
+    for (size_t c = 0; c < s->cells.size(); ++c) {
+        cell_start[c] = run;
+        for (int32_t id : s->cells[c]) ids[run++] = id;
     }
     cell_start[s->cells.size()] = run;
 }

@@ -7,12 +7,17 @@
  * legs may load it.  The product path (libsph_cuda.so, libsph_host.so) never
  * links, loads or calls anything in oracle/.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures and
- * cannot be compiled here (needs Qt5 + OpenCL headers), so this restatement is
- * pinned only by known answers derived from the reference source (particle
- * counts, constants, isolated-particle and lattice-interior densities; see
- * tests/test_oracle_known_answers.py) and by an independent numpy restatement
- * (tests/np_restatement.py) that must agree bit-for-bit on small scenes.
+ * PARITY PINNED against the reference's own code: oracle/_ref/libsph_ref.so is the reference's
+ * CCPUParticleSimulator / CBaseParticleSimulator / CCollisionGeometry / CGrid / CParticle compiled UNMODIFIED
+ * from /root/reference against stand-in Qt headers (oracle/qt_shim, oracle/ref_driver.cpp, Makefile target
+ * `ref`).  This restatement must reproduce it BIT FOR BIT every step — positions, velocities, densities,
+ * pressures, accelerations and the history-dependent order inside every grid cell — on BASELINE configs[0]
+ * (16 000 particles, 100 steps), the fountain, random states, tilted gravity, the wall and mesh bounce
+ * (tests/test_ref_pins_oracle.py), and against the committed vectors that library produced
+ * (tests/golden/ref_*.npz, tests/test_oracle_matches_ref_golden.py; these run where /root/reference is absent).
+ * The one piece that stays restated on both sides is Qt's QVector3D (QtGui is not in this image; its inline
+ * semantics are written out in oracle/qt_shim/qt_shim_core.h).  The reference ships no tests or golden vectors
+ * of its own; known answers derived from its source are in tests/test_oracle_known_answers.py.
  *
  * All citations are relative to /root/reference.
  */
@@ -38,6 +43,9 @@ void oracle_destroy(OracleSim *s);
 void oracle_setup_scene(OracleSim *s);
 /* replace the whole state: n particles, ids 0..n-1, xyz-interleaved fp32 */
 void oracle_set_state(OracleSim *s, int64_t n, const float *pos, const float *vel);
+/* overwrite positions / velocities of the existing particles and leave the cell vectors alone (what integrate()
+ * does): the next update_grid moves them with the history the cells already have.  -1 unless n == count */
+int oracle_overwrite_state(OracleSim *s, int64_t n, const float *pos, const float *vel);
 /* addParticle (src/CBaseParticleSimulator.cpp:67-74) */
 void oracle_add_particle(OracleSim *s, float x, float y, float z, float vx, float vy, float vz);
 void oracle_set_gravity(OracleSim *s, float gx, float gy, float gz);
@@ -85,6 +93,9 @@ void oracle_get_keys(const OracleSim *s, int32_t *outn);
 /* per-cell membership of the grid as updateGrid left it: cell_start[cells+1], ids[n] sorted by id inside each cell
  * (canonical (cell,id) permutation) */
 void oracle_get_cells(const OracleSim *s, int32_t *cell_start, int32_t *ids);
+/* the same membership in the order the cell vectors actually hold (push_back / swap-and-pop history,
+ * src/CCPUParticleSimulator.cpp:72-83): the traversal order of the density and force sums, compared with oracle/_ref */
+void oracle_get_cells_raw(const OracleSim *s, int32_t *cell_start, int32_t *ids);
 /* neighbour sets from the current grid: r2 <= h2, self included; counts[n]; if lists != NULL it must hold
  * sum(counts) ids, neighbours of particle 0 first, each list sorted ascending */
 int64_t oracle_get_neighbours(const OracleSim *s, int32_t *counts, int32_t *lists);

@@ -31,6 +31,7 @@ def _load():
         "oracle_destroy": (None, [vp]),
         "oracle_setup_scene": (None, [vp]),
         "oracle_set_state": (None, [vp, i64, vp, vp]),
+        "oracle_overwrite_state": (i32, [vp, i64, vp, vp]),
         "oracle_add_particle": (None, [vp, f, f, f, f, f, f]),
         "oracle_set_gravity": (None, [vp, f, f, f]),
         "oracle_set_faces": (None, [vp, i32, vp]),
@@ -59,6 +60,7 @@ def _load():
         "oracle_get_pressure": (None, [vp, vp]),
         "oracle_get_keys": (None, [vp, vp]),
         "oracle_get_cells": (None, [vp, vp, vp]),
+        "oracle_get_cells_raw": (None, [vp, vp, vp]),
         "oracle_get_neighbours": (i64, [vp, vp, vp]),
         "oracle_stats": (None, [vp, vp]),
     }
@@ -106,6 +108,14 @@ class Oracle:
         pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
         vel = np.zeros_like(pos) if vel is None else np.ascontiguousarray(vel, dtype=np.float32).reshape(-1, 3)
         lib().oracle_set_state(self._h, pos.shape[0], _p(pos), _p(vel))
+        return self
+
+    def overwrite_state(self, pos, vel):
+        """New positions / velocities for the existing particles; cell vectors keep their history."""
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        vel = np.ascontiguousarray(vel, dtype=np.float32).reshape(-1, 3)
+        if lib().oracle_overwrite_state(self._h, pos.shape[0], _p(pos), _p(vel)) != 0:
+            raise ValueError("overwrite_state: n must equal the current count")
         return self
 
     def add_particle(self, x, y, z, vx=0.0, vy=0.0, vz=0.0):
@@ -203,6 +213,13 @@ class Oracle:
         cs = np.empty(self.n_cells + 1, dtype=np.int32)
         ids = np.empty(self.n, dtype=np.int32)
         lib().oracle_get_cells(self._h, _p(cs), _p(ids))
+        return cs, ids
+
+    def cells_raw(self):
+        """(cell_start[cells+1], ids[n]) in the cell vectors' own (swap-and-pop history) order."""
+        cs = np.empty(self.n_cells + 1, dtype=np.int32)
+        ids = np.empty(self.n, dtype=np.int32)
+        lib().oracle_get_cells_raw(self._h, _p(cs), _p(ids))
         return cs, ids
 
     def neighbours(self, lists=True):

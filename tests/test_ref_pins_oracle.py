@@ -1,0 +1,222 @@
+"""The oracle answers to the reference's own code.
+
+oracle/_ref/libsph_ref.so is the reference's CCPUParticleSimulator / CBaseParticleSimulator /
+CCollisionGeometry / CGrid / CParticle compiled UNMODIFIED from /root/reference against oracle/qt_shim
+(oracle/Makefile target `ref`).  These tests require the hand restatement oracle/sph_oracle.cpp to reproduce
+it BIT FOR BIT — positions, velocities, densities, pressures, accelerations and even the history-dependent
+order inside every grid cell — every step, on BASELINE configs[0] (dam break, 16 000 particles) and on the
+fountain.  Where the library is absent (a box without /root/reference and without the built file) the live
+tests skip and test_oracle_matches_ref_golden.py checks the committed vectors the library produced.
+"""
+import numpy as np
+import pytest
+
+import ref_binding
+from oracle_binding import DAM_BREAK, FOUNTAIN, Oracle
+
+pytestmark = pytest.mark.skipif(not ref_binding.available(), reason="oracle/_ref not built and /root/reference absent")
+
+FIELDS = ("pos", "vel", "acc", "density", "pressure")
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def assert_same_state(r, o, where):
+    assert r.n == o.n, where
+    for name in FIELDS:
+        a, b = bits(getattr(r, name)), bits(getattr(o, name))
+        assert np.array_equal(a, b), f"{where}: {name} differs in {(a != b).sum()} words"
+    ca, ia = r.cells()
+    cb, ib = o.cells_raw()
+    assert np.array_equal(ca, cb), f"{where}: cell_start differs"
+    assert np.array_equal(ia, ib), f"{where}: intra-cell order differs"
+
+
+def test_scene_sizes_grid_constants_and_walls():
+    """setupScene / ctor (src/CBaseParticleSimulator.cpp:3-65) for the ten slider positions 0.1 .. 1.0."""
+    counts = []
+    for k in range(1, 11):
+        box = k / 10.0
+        r = ref_binding.Reference(box).setup_scene()
+        o = Oracle(box).setup_scene()
+        counts.append(r.n)
+        assert (r.n, r.max_count, r.grid_res) == (o.n, o.max_count, o.grid_res)
+        assert np.array_equal(bits(r.pos), bits(o.pos))
+        half = np.float32(np.float32(box) / np.float32(2.0))
+        w = r.walls
+        assert np.array_equal(w[:, :3], np.vstack([-np.eye(3), np.eye(3)]).astype(np.float32))
+        assert np.array_equal(np.abs(w[:, 3:]).sum(axis=1), np.full(6, half, dtype=np.float32))
+    assert counts == [50, 243, 784, 1620, 2904, 5103, 7688, 11664, 16000, 21296]
+    r = ref_binding.Reference(0.4)
+    poly6, spiky, visc, _ = Oracle(0.4).constants()
+    assert np.array_equal(r.params, np.array([poly6, spiky, visc], dtype=np.float32))
+    assert r.dt == np.float32(0.01)
+    assert r.device_name == "CPU (without OpenCL)"
+
+
+def test_config0_dam_break_16000_100_steps_bit_identical():
+    """BASELINE configs[0]: dam break, box 0.9 -> 16 000 particles, 100 steps, every step compared."""
+    r = ref_binding.Reference(0.9).setup_scene()
+    o = Oracle(0.9).setup_scene()
+    assert r.n == 16000
+    for step in range(100):
+        r.step()
+        o.step()
+        assert_same_state(r, o, f"step {step}")
+
+
+def test_phase_by_phase_box_0p4():
+    """The five phases called one by one (the virtuals CBaseParticleSimulator::step sequences)."""
+    r = ref_binding.Reference(0.4).setup_scene()
+    o = Oracle(0.4).setup_scene()
+    for step in range(30):
+        for phase in ("update_grid", "update_density_pressure", "update_forces", "update_collisions", "integrate"):
+            getattr(r, phase)()
+            getattr(o, phase)()
+            assert_same_state(r, o, f"step {step} after {phase}")
+
+
+def test_fountain_box_0p4_150_steps_bit_identical():
+    """generateParticles (src/CBaseParticleSimulator.cpp:187-210) + the step, fountain scene, box 0.4."""
+    r = ref_binding.Reference(0.4, FOUNTAIN).setup_scene()
+    o = Oracle(0.4, FOUNTAIN).setup_scene()
+    assert r.n == 0 and r.max_count == o.max_count == 1620
+    for step in range(150):
+        r.step()
+        o.step()
+        assert_same_state(r, o, f"step {step}")
+    assert r.n == 7 * 150
+
+
+def test_fountain_stops_emitting_at_the_cap():
+    r = ref_binding.Reference(0.2, FOUNTAIN).setup_scene()
+    o = Oracle(0.2, FOUNTAIN).setup_scene()
+    for step in range(45):
+        r.step()
+        o.step()
+        assert r.n == o.n, step
+    assert r.n == 238  # max 243: emission stops once count >= 243 - 7
+    assert_same_state(r, o, "after the cap")
+
+
+def test_random_states_bit_identical():
+    """Irregular states (not reachable from the lattice in a few steps): random positions incl. particles outside
+    the box, exactly on cell faces and in a dense clump, random velocities; two full steps from each."""
+    rng = np.random.default_rng(0xC0FFEE)
+    box = 0.5
+    r = ref_binding.Reference(box).setup_scene()
+    o = Oracle(box).setup_scene()
+    n = r.n
+    for trial in range(4):
+        pos = rng.uniform(-0.27, 0.27, size=(n, 3)).astype(np.float32)
+        pos[:64] = (np.floor(pos[:64] / np.float32(0.0457)) * np.float32(0.0457)).astype(np.float32)  # on faces
+        pos[64:200] *= np.float32(0.3)  # a dense clump
+        vel = rng.normal(0, 1.5, size=(n, 3)).astype(np.float32)
+        r.set_state(pos, vel)
+        o.overwrite_state(pos, vel)
+        for step in range(2):
+            r.step()
+            o.step()
+            assert_same_state(r, o, f"trial {trial} step {step}")
+
+
+def test_gravity_keys_and_toggle():
+    """onKeyPressed / toggleGravity (src/CBaseParticleSimulator.cpp:94-114,154-179)."""
+    r = ref_binding.Reference(0.2).setup_scene()
+    g0 = np.array([0, -9.80665, 0], dtype=np.float32)
+    assert np.array_equal(r.gravity, g0)
+    r.key(ref_binding.KEY_O)
+    assert np.array_equal(r.gravity, g0 + np.array([-1, 0, 0], dtype=np.float32))
+    r.key(ref_binding.KEY_P)
+    r.key(ref_binding.KEY_P)
+    assert np.array_equal(r.gravity, g0 + np.array([1, 0, 0], dtype=np.float32))
+    r.key(ref_binding.KEY_G)
+    assert np.array_equal(r.gravity, np.zeros(3, dtype=np.float32))
+    r.key(ref_binding.KEY_G)
+    assert np.array_equal(r.gravity, g0)  # toggling back restores (0, g, 0), the x tilt is lost
+    assert not r.running
+    r.key(ref_binding.KEY_SPACE)
+    assert r.running
+    r.key(ref_binding.KEY_SPACE)
+    assert not r.running
+    before = r.pos
+    r.key(ref_binding.KEY_S)  # a single step through doWork(), which emits iterationChanged(totalIteration)
+    assert ref_binding.lib().ref_last_iteration() == 1
+    assert not np.array_equal(before, r.pos)
+
+
+def test_tilted_gravity_step_matches_oracle():
+    r = ref_binding.Reference(0.4).setup_scene()
+    o = Oracle(0.4).setup_scene()
+    r.step(5)
+    o.step(5)
+    r.key(ref_binding.KEY_O)
+    r.key(ref_binding.KEY_O)
+    o.set_gravity(r.gravity)
+    for step in range(10):
+        r.step()
+        o.step()
+        assert_same_state(r, o, f"tilted step {step}")
+    r.key(ref_binding.KEY_G)
+    o.set_gravity((0, 0, 0))
+    r.step(3)
+    o.step(3)
+    assert_same_state(r, o, "zero gravity")
+
+
+def test_wall_bounce_on_random_inputs():
+    """inverseBoundingBoxBounce (src/CCollisionGeometry.cpp:117-133) against the oracle's wall term."""
+    rng = np.random.default_rng(7)
+    box = 0.4
+    r = ref_binding.Reference(box).setup_scene()
+    n = r.n
+    pos = rng.uniform(-0.23, 0.23, size=(n, 3)).astype(np.float32)
+    vel = rng.normal(0, 3, size=(n, 3)).astype(np.float32)
+    o = Oracle(box)
+    o.set_state(pos, vel)
+    o.update_grid(); o.update_density_pressure(); o.update_forces()
+    wall = o.acc_wall
+    for i in range(0, n, 3):
+        assert np.array_equal(bits(r.wall_bounce(pos[i], vel[i])), bits(wall[i])), i
+
+
+def cuboid_faces(box):
+    """The 12 triangles CCollisionGeometry::init() reads out of the cuboid (qt_shim QCuboidGeometry layout):
+    rows of normal, v0, v1, v2."""
+    e = np.float32(box) / np.float32(2.0)
+    planes = [(2, 1, 0, 1.0), (2, 1, 0, -1.0), (0, 2, 1, 1.0), (0, 2, 1, -1.0), (0, 1, 2, 1.0), (0, 1, 2, -1.0)]
+    faces = []
+    for a_ax, b_ax, n_ax, sign in planes:
+        verts = []
+        for j in range(2):
+            for i in range(2):
+                p = np.zeros(3, dtype=np.float32)
+                p[a_ax] = -e + np.float32(i) * np.float32(box)
+                p[b_ax] = -e + np.float32(j) * np.float32(box)
+                p[n_ax] = np.float32(sign) * e
+                verts.append(p)
+        nrm = np.zeros(3, dtype=np.float32)
+        nrm[n_ax] = sign
+        for tri in ((0, 1, 3), (0, 3, 2)):
+            faces.append(np.concatenate([nrm] + [verts[k] for k in tri]))
+    return np.array(faces, dtype=np.float32)
+
+
+def test_mesh_bounce_matches_oracle_row_f4():
+    """inverseBounce (src/CCollisionGeometry.cpp:97-115): prepared by the reference, never called by its step —
+    the oracle's restatement (row f4) against the real function on the cuboid's own faces."""
+    rng = np.random.default_rng(11)
+    box = 0.4
+    r = ref_binding.Reference(box).setup_scene()
+    n = 400
+    pos = rng.uniform(-0.22, 0.22, size=(n, 3)).astype(np.float32)
+    vel = rng.normal(0, 3, size=(n, 3)).astype(np.float32)
+    o = Oracle(box)
+    o.set_state(pos, vel)
+    o.set_faces(cuboid_faces(box))
+    o.update_grid(); o.update_density_pressure(); o.update_forces()
+    mesh = o.acc_mesh
+    for i in range(n):
+        assert np.array_equal(bits(r.mesh_bounce(pos[i], vel[i])), bits(mesh[i])), i
