@@ -17,6 +17,7 @@ from .binding import (  # noqa: F401
     SphError,
     build,
     comm_unique_id,
+    simulation_type,
     slab_plan,
     cuda_lib,
     declared_symbols,

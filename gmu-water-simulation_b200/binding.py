@@ -100,6 +100,8 @@ def cuda_lib():
             "sph_last_error": (C.c_char_p, [vp]),
             "sph_upload_particles": (i32, [vp, vp, u32]),
             "sph_append_particles": (i32, [vp, vp, u32]),
+            "sph_set_emitter": (i32, [vp, vp, u32, u32, u32]),
+            "sph_emit": (i32, [vp, P(u32)]),
             "sph_download_particles": (i32, [vp, vp, u32, P(u32)]),
             "sph_download_particles_async": (i32, [vp, vp, u32]),
             "sph_download_wait": (i32, [vp, P(u32)]),
@@ -119,10 +121,12 @@ def cuda_lib():
             "sph_download_cell_start": (i32, [vp, vp]),
             "sph_download_density_pressure_accel": (i32, [vp, vp, vp, vp]),
             "sph_download_neighbours": (i32, [vp, vp, vp, u64, P(u64)]),
+            "sph_download_mask_neighbours": (i32, [vp, vp, vp, u64, P(u64)]),
             "sph_brute_density_pressure": (i32, [vp, P(dbl)]),
             "sph_brute_forces": (i32, [vp, P(dbl)]),
             "sph_brute_neighbour_counts": (i32, [vp, vp]),
             "sph_stats": (i32, [vp, vp]),
+            "sph_fill_height_percentile": (i32, [vp, dbl, P(dbl)]),
             "sph_set_option": (i32, [vp, C.c_char_p, i32]),
             "sph_get_counter": (i32, [vp, C.c_char_p, P(u64)]),
             "sph_comm_unique_id": (i32, [vp]),
@@ -164,6 +168,11 @@ def host_lib():
             "gmu_sim_set_gravity": (i32, [vp, f, f, f]),
             "gmu_sim_set_collision_faces": (i32, [vp, vp, i32]),
             "gmu_sim_key": (i32, [vp, i32]),
+            "gmu_sim_get_gravity": (i32, [vp, vp]),
+            "gmu_sim_is_running": (i32, [vp]),
+            "gmu_sim_push_event": (i32, [vp, vp]),
+            "gmu_sim_type_from_name": (i32, [C.c_char_p]),
+            "gmu_sim_create_by_type": (vp, [i32, f, f, f, i32, i32]),
             "gmu_sim_set_profiling": (i32, [vp, i32, i32]),
             "gmu_sim_set_emission_multiplier": (i32, [vp, i32]),
             "gmu_sim_particle_count": (u64, [vp]),
@@ -185,6 +194,11 @@ def host_lib():
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def simulation_type(combo_text):
+    """eSimulationType value of a simulation-type combo text ("GPU Grid" -> 0 ... "CUDA Grid" -> 3); -1 if unknown."""
+    return int(host_lib().gmu_sim_type_from_name(combo_text.encode()))
 
 
 def device_count():
@@ -293,6 +307,16 @@ class SphContext:
         rec = np.ascontiguousarray(rec, dtype=PARTICLE_DTYPE)
         self._ck(self.lib.sph_append_particles(self._h, _ptr(rec), rec.shape[0]))
 
+    def set_emitter(self, templates, group=7, max_count=None):
+        rec = np.ascontiguousarray(templates, dtype=PARTICLE_DTYPE)
+        self._ck(self.lib.sph_set_emitter(self._h, _ptr(rec) if rec.shape[0] else None, rec.shape[0], int(group),
+                                          int(self.cfg.max_particles if max_count is None else max_count)))
+
+    def emit(self):
+        got = C.c_uint32(0)
+        self._ck(self.lib.sph_emit(self._h, C.byref(got)))
+        return got.value
+
     def download(self, out=None):
         n = self.n
         if out is None:
@@ -384,16 +408,23 @@ class SphContext:
         self._ck(self.lib.sph_download_density_pressure_accel(self._h, _ptr(rho), _ptr(prs), _ptr(acc)))
         return rho, prs, acc
 
-    def neighbours(self, lists=True):
+    def neighbours(self, lists=True, source="walk"):
+        """source="walk": the validation kernel that re-evaluates the predicate over the 27 cells;
+        source="mask": the production hit words of the density pass (what the force pass consumes), decoded."""
+        fn = self.lib.sph_download_mask_neighbours if source == "mask" else self.lib.sph_download_neighbours
         n = self.n
         counts = np.empty(n, dtype=np.int32)
         total = C.c_uint64(0)
-        self._ck(self.lib.sph_download_neighbours(self._h, _ptr(counts), None, 0, C.byref(total)))
+        self._ck(fn(self._h, _ptr(counts), None, 0, C.byref(total)))
         if not lists:
             return counts, None
         flat = np.empty(total.value, dtype=np.int32)
-        self._ck(self.lib.sph_download_neighbours(self._h, _ptr(counts), _ptr(flat), total.value, C.byref(total)))
+        self._ck(fn(self._h, _ptr(counts), _ptr(flat), total.value, C.byref(total)))
         return counts, flat
+
+    @property
+    def uses_mask_passes(self):
+        return self.grid_res[0] >= 4
 
     def brute_neighbour_counts(self):
         out = np.empty(self.n, dtype=np.int32)
@@ -403,7 +434,12 @@ class SphContext:
     def stats(self):
         out = np.zeros(6, dtype=np.float64)
         self._ck(self.lib.sph_stats(self._h, _ptr(out)))
-        return dict(ke=out[0], com=out[1:4].copy(), fill=out[4], mean_speed=out[5])
+        return dict(ke=out[0], com=out[1:4].copy(), fill=out[4], mean_speed=out[5])  # 95th percentile: fill_height_percentile()
+
+    def fill_height_percentile(self, q=0.95):
+        out = C.c_double(0)
+        self._ck(self.lib.sph_fill_height_percentile(self._h, float(q), C.byref(out)))
+        return out.value
 
     def set_option(self, name, value):
         self._ck(self.lib.sph_set_option(self._h, name.encode(), int(value)))
@@ -450,12 +486,16 @@ class Simulator:
     """The C++ simulator object (CCUDAParticleSimulator / scene-only) through the facade."""
 
     def __init__(self, kind="cuda", box=0.9, device=0, scenario=DAM_BREAK):
+        """kind: "cuda" | "cuda_brute" | "scene_only", or an eSimulationType value (int) for the factory path."""
         self.lib = host_lib()
         if np.isscalar(box):
             box = (box, box, box)
         self.box = tuple(float(np.float32(b)) for b in box)
         self.kind = kind
-        self._h = self.lib.gmu_sim_create(kind.encode(), *self.box, int(device), int(scenario))
+        if isinstance(kind, int):
+            self._h = self.lib.gmu_sim_create_by_type(kind, *self.box, int(device), int(scenario))
+        else:
+            self._h = self.lib.gmu_sim_create(kind.encode(), *self.box, int(device), int(scenario))
         if not self._h:
             raise SphError(self.lib.gmu_sim_last_error().decode())
 
@@ -515,6 +555,20 @@ class Simulator:
 
     def key(self, qt_key):
         self._ck(self.lib.gmu_sim_key(self._h, int(qt_key)))
+
+    @property
+    def gravity(self):
+        out = np.zeros(3, dtype=np.float32)
+        self._ck(self.lib.gmu_sim_get_gravity(self._h, _ptr(out)))
+        return out
+
+    @property
+    def running(self):
+        return bool(self.lib.gmu_sim_is_running(self._h))
+
+    def push_event(self, iteration, fps, grid, density, forces, collisions, integrate):
+        ev = np.array([iteration, fps, grid, density, forces, collisions, integrate], dtype=np.float64)
+        self._ck(self.lib.gmu_sim_push_event(self._h, _ptr(ev)))
 
     def set_profiling(self, on=True, stride=10):
         self._ck(self.lib.gmu_sim_set_profiling(self._h, int(on), int(stride)))

@@ -68,27 +68,46 @@ void CBaseParticleSimulator::addParticle(float x, float y, float z, cl_float3 in
     m_particlesCount++;
 }
 
+void CBaseParticleSimulator::nozzlePattern(int nozzle, float out[7][3]) const {
+    // :195-206 — the seven positions one nozzle emits, on the box floor.  One nozzle sits at the origin like the
+    // reference's; with more nozzles (extension) they form a centred square array 3h apart so their particles never
+    // coincide.
+    const float halfParticle = CParticle::h / 2.0f;
+    const QVector3D offset = -m_boxSize / 2.0f;
+    const int side = (int)std::ceil(std::sqrt((double)m_emissionMultiplier));
+    const float cx = 3.0f * CParticle::h * ((float)(nozzle % side) - 0.5f * (float)(side - 1));
+    const float cz = 3.0f * CParticle::h * ((float)(nozzle / side) - 0.5f * (float)(side - 1));
+    const float dx[7] = {0, -halfParticle, halfParticle, -CParticle::h / 4, CParticle::h / 4, -CParticle::h / 4, CParticle::h / 4};
+    const float dz[7] = {0, 0, 0, -halfParticle, -halfParticle, halfParticle, halfParticle};
+    for (int k = 0; k < 7; ++k) {
+        out[k][0] = cx + dx[k];
+        out[k][1] = offset.y();
+        out[k][2] = cz + dz[k];
+    }
+}
+
+std::vector<CParticle::Physics> CBaseParticleSimulator::emissionTemplate() const {
+    std::vector<CParticle::Physics> tpl;
+    if (m_scenario != FOUNTAIN) return tpl;
+    const cl_float3 initialVelocity = {0.0f, m_boxSize.y() * 3.2f, 0.0f, 0.0f};
+    for (int nozzle = 0; nozzle < m_emissionMultiplier; ++nozzle) {
+        float p[7][3];
+        nozzlePattern(nozzle, p);
+        for (int k = 0; k < 7; ++k) tpl.emplace_back(p[k][0], p[k][1], p[k][2], 0u, initialVelocity);
+    }
+    return tpl;
+}
+
 void CBaseParticleSimulator::generateParticles() {
     // :187-210 — seven particles per nozzle per step at the box floor, shot upwards
     if (m_scenario != FOUNTAIN) return;
     const int particlesPerIteration = 7;
-    const float halfParticle = CParticle::h / 2.0f;
-    const QVector3D offset = -m_boxSize / 2.0f;
     const cl_float3 initialVelocity = {0.0f, m_boxSize.y() * 3.2f, 0.0f, 0.0f};
     for (int nozzle = 0; nozzle < m_emissionMultiplier; ++nozzle) {
         if (m_nextParticleId >= (m_maxParticlesCount - (cl_uint)particlesPerIteration)) return;
-        // one nozzle sits at the origin like the reference's; with more nozzles (extension) they form a
-        // centred square array 3h apart so their particles never coincide
-        const int side = (int)std::ceil(std::sqrt((double)m_emissionMultiplier));
-        const float cx = 3.0f * CParticle::h * ((float)(nozzle % side) - 0.5f * (float)(side - 1));
-        const float cz = 3.0f * CParticle::h * ((float)(nozzle / side) - 0.5f * (float)(side - 1));
-        addParticle(cx + 0, offset.y(), cz + 0, initialVelocity);
-        addParticle(cx + -halfParticle, offset.y(), cz + 0, initialVelocity);
-        addParticle(cx + halfParticle, offset.y(), cz + 0, initialVelocity);
-        addParticle(cx + -CParticle::h / 4, offset.y(), cz + -halfParticle, initialVelocity);
-        addParticle(cx + CParticle::h / 4, offset.y(), cz + -halfParticle, initialVelocity);
-        addParticle(cx + -CParticle::h / 4, offset.y(), cz + halfParticle, initialVelocity);
-        addParticle(cx + CParticle::h / 4, offset.y(), cz + halfParticle, initialVelocity);
+        float p[7][3];
+        nozzlePattern(nozzle, p);
+        for (int k = 0; k < 7; ++k) addParticle(p[k][0], p[k][1], p[k][2], initialVelocity);
     }
 }
 

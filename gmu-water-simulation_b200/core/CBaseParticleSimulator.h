@@ -74,9 +74,13 @@ public:
     unsigned long getTotalIteration() const { return totalIteration; }
     QVector3D getBoxSize() const { return m_boxSize; }
     QVector3D getGravityVector() const { return gravity; }
+    bool running() { return isRunning(); }
     const std::vector<CParticle::Physics> &getHostParticles() const { return m_clParticles; }
     // fountain: number of 7-particle nozzles fired per step (1 = the reference's behaviour)
-    void setEmissionMultiplier(int nozzles) { m_emissionMultiplier = nozzles < 1 ? 1 : nozzles; }
+    virtual void setEmissionMultiplier(int nozzles) { m_emissionMultiplier = nozzles < 1 ? 1 : nozzles; }
+    int emissionMultiplier() const { return m_emissionMultiplier; }
+    // the records ONE step of the fountain appends (ids unset), in emission order: 7 per nozzle
+    std::vector<CParticle::Physics> emissionTemplate() const;
     // slab decomposition: keep only the particles of z-layers [z0, z1) when the scene is generated
     void setOwnedLayers(int z0, int z1) { m_ownedZ0 = z0; m_ownedZ1 = z1; }
 
@@ -118,11 +122,14 @@ protected:
     // true when this step's phase durations will be logged (every eventLoggerStride-th iteration)
     bool sampleThisStep() const { return m_profiling && eventLoggerStride > 0 && totalIteration % (unsigned long)eventLoggerStride == 0; }
     void addIterations(unsigned long k) { totalIteration += k; iterationSincePaused += k; }
+    // the emission at the top of step() on its own (host mirror only): for subclasses that emit on the device
+    void emitParticles() { generateParticles(); }
 
 private:
     void init(SimulationScenario scenario);
     void addParticle(float x, float y, float z, cl_float3 initialVelocity = {0, 0, 0, 0});
     void generateParticles();
+    void nozzlePattern(int nozzle, float out[7][3]) const;
 
     QTimer m_timer;
     QElapsedTimer m_elapsed_timer;

@@ -68,6 +68,7 @@ void CCUDAParticleSimulator::setupScene() {
         sph_pin_host_buffer(m_cuda->ctx(), m_clParticles.data(), m_clParticles.capacity() * sizeof(CParticle::Physics));
 
     pushCollisionFaces();
+    pushEmitter();
 
     m_deviceCount = 0;
     m_cuda->check(sph_upload_particles(m_cuda->ctx(), reinterpret_cast<const sph_particle *>(m_clParticles.data()),
@@ -96,6 +97,32 @@ void CCUDAParticleSimulator::pushCollisionFaces() {
         }
     }
     m_cuda->check(sph_set_collision_faces(m_cuda->ctx(), flat.data(), (uint32_t)flat.size()), "collision faces");
+}
+
+void CCUDAParticleSimulator::setEmissionMultiplier(int nozzles) {
+    CBaseParticleSimulator::setEmissionMultiplier(nozzles);
+    if (m_cuda) pushEmitter();
+}
+
+void CCUDAParticleSimulator::pushEmitter() {
+    // generateParticles() as device templates (fountain only): stepMany() then emits without touching PCIe
+    if (m_slab) return;
+    const std::vector<CParticle::Physics> tpl = emissionTemplate();
+    m_cuda->check(sph_set_emitter(m_cuda->ctx(), reinterpret_cast<const sph_particle *>(tpl.data()), (uint32_t)tpl.size(), 7,
+                                  m_maxParticlesCount), "emitter");
+}
+
+// Fountain batches: the device appends the new particles itself (sph_set_emitter) and runs the fused step; the host
+// applies the same emission rule to its mirror, so ids and counts stay in lock-step without any per-step upload.
+void CCUDAParticleSimulator::stepManyFountain(int steps, double *deviceMs) {
+    pushNewParticles();  // anything step() emitted on the host but has not sent yet
+    m_cuda->check(sph_step(m_cuda->ctx(), steps, deviceMs), "stepMany (fountain)");
+    for (int k = 0; k < steps; ++k) emitParticles();
+    m_deviceCount = (cl_uint)m_particlesCount;
+    uint32_t n = 0;
+    sph_particle_count(m_cuda->ctx(), &n);
+    if (n != m_deviceCount) throw CUDAException("fountain: device and host emission counts disagree");
+    addIterations((unsigned long)steps);
 }
 
 void CCUDAParticleSimulator::pushNewParticles() {
@@ -140,13 +167,21 @@ void CCUDAParticleSimulator::step() {
 
 void CCUDAParticleSimulator::stepMany(int steps, double *deviceMs) {
     if (!m_cuda) throw CUDAException("stepMany before setupScene");
-    if ((m_scenario == FOUNTAIN || m_brute) && !m_slab) {  // emission / all-pairs go through the phase path
+    // The mirror modes keep their meaning across a batch: in RoundTrip the host vector is canonical, so it goes up
+    // first; in every non-resident mode the mirror shows the state after the batch (one read-back, not one per step).
+    if (m_mirrorMode == RoundTrip && !m_slab)
+        m_cuda->check(sph_upload_particles(m_cuda->ctx(), reinterpret_cast<const sph_particle *>(m_clParticles.data()), m_deviceCount),
+                      "stepMany upload");
+    if (m_brute && !m_slab) {  // all-pairs semantics go through the phase path
         for (int k = 0; k < steps; ++k) { CBaseParticleSimulator::step(); addIterations(1); }
         if (deviceMs) { m_cuda->check(sph_synchronize(m_cuda->ctx()), "stepMany"); *deviceMs = 0.0; }
-        return;
+    } else if (m_scenario == FOUNTAIN && !m_slab) {
+        stepManyFountain(steps, deviceMs);
+    } else {
+        m_cuda->check(sph_step(m_cuda->ctx(), steps, deviceMs), "stepMany");
+        addIterations((unsigned long)steps);
     }
-    m_cuda->check(sph_step(m_cuda->ctx(), steps, deviceMs), "stepMany");
-    addIterations((unsigned long)steps);
+    if (m_mirrorMode != Resident && steps > 0) syncHostMirror();
 }
 
 void CCUDAParticleSimulator::setMirrorMode(MirrorMode m) {

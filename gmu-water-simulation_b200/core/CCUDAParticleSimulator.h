@@ -45,6 +45,7 @@ public:
     void setMirrorStride(int stride) { m_mirrorStride = stride < 1 ? 1 : stride; }
     // collision mesh for CCollisionGeometry::inverseBounce (row f4); may be called before or after setupScene
     void setCollisionFaces(const std::vector<sFace> &faces);
+    void setEmissionMultiplier(int nozzles) override;       // also re-arms the device-side emitter
     void setBruteForce(bool on) { m_brute = on; }          // CGPUBruteParticleSimulator semantics (all pairs)
     // Multi-GPU extension: make this instance rank `rank` of `world` z-slabs (call before setupScene).  ncclId is
     // the 128-byte id from sph_comm_unique_id(), identical on all ranks.  In slab mode the host mirror holds this
@@ -64,6 +65,8 @@ protected:
 private:
     void pushNewParticles();
     void pushCollisionFaces();
+    void pushEmitter();
+    void stepManyFountain(int steps, double *deviceMs);
 
     bool m_slab = false;
     int m_rank = 0, m_world = 1, m_z0 = 0, m_z1 = 0;

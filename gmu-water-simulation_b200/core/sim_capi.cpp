@@ -153,6 +153,15 @@ int gmu_sim_set_collision_faces(gmu_sim *s, const float *f, int n_faces) {
     });
 }
 
+int gmu_sim_get_gravity(gmu_sim *s, float *out3) {
+    return guarded([&] {
+        const QVector3D g = H(s)->sim->getGravityVector();
+        out3[0] = g.x(); out3[1] = g.y(); out3[2] = g.z();
+    });
+}
+
+int gmu_sim_is_running(gmu_sim *s) { return H(s)->sim->running() ? 1 : 0; }
+
 int gmu_sim_key(gmu_sim *s, int qt_key) { return guarded([&] { H(s)->sim->onKeyPressed((Qt::Key)qt_key); }); }
 
 int gmu_sim_set_profiling(gmu_sim *s, int on, int stride) {
@@ -201,6 +210,37 @@ uint64_t gmu_sim_get_events(gmu_sim *s, double *out, uint64_t max_events) {
         o[4] = e.updateForces; o[5] = e.updateCollisions; o[6] = e.integrate;
     }
     return n;
+}
+
+int gmu_sim_push_event(gmu_sim *s, const double *ev7) {
+    // appends one profiling record (iteration, fps, grid, density, forces, collisions, integrate): lets a caller
+    // merge samples measured elsewhere into the log, and the tests pin the CSV layout with known numbers
+    return guarded([&] {
+        sProfilingEvent e((unsigned long)ev7[0]);
+        e.fps = ev7[1]; e.updateGrid = ev7[2]; e.updateDensityPressure = ev7[3]; e.updateForces = ev7[4];
+        e.updateCollisions = ev7[5]; e.integrate = ev7[6];
+        H(s)->sim->events << e;
+    });
+}
+
+int gmu_sim_type_from_name(const char *combo_text) {
+    for (int t = 0; t <= (int)eSimulationType::CUDABrute; ++t)
+        if (std::string(simulationTypeName((eSimulationType)t)) == (combo_text ? combo_text : "")) return t;
+    return -1;
+}
+
+gmu_sim *gmu_sim_create_by_type(int type, float bx, float by, float bz, int device, int scenario) {
+    Handle *h = new Handle();
+    int rc = guarded([&] {
+        h->sim = createSimulator((eSimulationType)type, &h->scene, QVector3D(bx, by, bz), device, (SimulationScenario)scenario);
+        h->cuda = static_cast<CCUDAParticleSimulator *>(h->sim);  // createSimulator only returns CUDA simulators
+    });
+    if (rc) {
+        delete h;
+        return nullptr;
+    }
+    h->sim->onErrorOccured([h](const char *what) { h->last_error = what; ++h->errors; });
+    return reinterpret_cast<gmu_sim *>(h);
 }
 
 int gmu_sim_export_logs(gmu_sim *s, const char *dir, const char *sim_name) {

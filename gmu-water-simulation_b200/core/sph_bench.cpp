@@ -85,7 +85,7 @@ int main(int argc, char **argv) {
                     "\"forces\": %.4f, \"collisions\": %.4f, \"integrate\": %.4f}, \"mirror\": %d, \"brute\": %s}\n",
                     scenario.c_str(), box[0], box[1], box[2], sim->getParticlesCount(), steps, sec, particle_steps / sec,
                     1e3 * sec / steps, ph[0] / ne, ph[1] / ne, ph[2] / ne, ph[3] / ne, ph[4] / ne, mirror, brute ? "true" : "false");
-        if (!csv.empty()) exportLogs(*sim, csv, brute ? "CUDA Brute" : "CUDA Grid");  // needs --phases to have samples
+        if (!csv.empty()) exportLogs(*sim, csv, simulationTypeName(brute ? eSimulationType::CUDABrute : eSimulationType::CUDAGrid));  // needs --phases to have samples
     } catch (const std::exception &e) {
         std::fprintf(stderr, "fatal: %s\n", e.what());
         return 1;

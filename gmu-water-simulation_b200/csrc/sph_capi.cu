@@ -51,6 +51,8 @@ struct sph_context {
     int *d_tmp_i32 = nullptr;  // [cap] scratch for by-id taps
     float *d_tmp_f32 = nullptr;  // [5*cap]
     double *d_stats = nullptr;
+    int *d_id_error = nullptr;  // set by the upload kernel when a record's id is >= max_particles (ABI precondition)
+    unsigned *d_hist = nullptr;  // [kHistBins] fill-height histogram (sph_fill_height_percentile)
     cudaGraphExec_t graph_exec = nullptr;
     uint32_t graph_n = 0;
     uint32_t last_step_n = 0xffffffffu;
@@ -69,6 +71,9 @@ struct sph_context {
     float4 *d_flush = nullptr;
     size_t flush_count = 0;
     std::vector<cudaEvent_t> step_events;
+    // device-side fountain emitter (sph_set_emitter): templates of the records one step appends
+    float4 *d_emit_pos = nullptr, *d_emit_vel = nullptr;
+    uint32_t emit_templates = 0, emit_group = 0, emit_max = 0;
     // slab mode (multi-GPU): this rank's z-range, exchange buffers and NCCL communicator
     struct Slab *slab = nullptr;
     uint32_t in_off = 0;  // the next grid build reads A[in_off, in_off + n)
@@ -255,7 +260,23 @@ void drop_graph(sph_context *c) {
 // pos/vel arrays the taps should read: S between update_grid and integrate, A otherwise
 const float4 *view_pos(const sph_context *c) { return c->a_aligned || !c->s_valid ? c->pos_a : c->pos_s; }
 const float4 *view_vel(const sph_context *c) { return c->a_aligned || !c->s_valid ? c->vel_a : c->vel_s; }
-bool aux_aligned(const sph_context *c) { return c->s_valid; }  // dp/acc/key_s index == view index
+// dp/acc/key_s index == view index; a new grid build invalidates last step's density / forces until they are recomputed
+bool aux_aligned(const sph_context *c) { return c->s_valid; }
+const float4 *aux_dp(const sph_context *c) { return (c->s_valid && c->density_valid) ? c->dp : nullptr; }
+const float4 *aux_acc(const sph_context *c) { return (c->s_valid && c->forces_valid) ? c->acc : nullptr; }
+
+// By-id read-backs index host arrays with the particle ids: they need the ids to be < max_particles (checked by the
+// upload kernel) and, to fill every slot, a permutation of 0..n-1.  Called after the tap's own stream sync.
+int id_precondition(sph_context *c, const char *who) {
+    int flag = 0;
+    cudaError_t e = cudaMemcpyAsync(&flag, c->d_id_error, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return fail(c, SPH_ERR_CUDA, std::string("CUDA::") + cudaGetErrorName(e) + " | id check");
+    if (flag)
+        return fail(c, SPH_ERR_ARGUMENT, std::string(who) + ": an uploaded particle id is >= max_particles; by-id read-backs "
+                                         "need unique ids below max_particles (a permutation of 0..n-1 fills every slot)");
+    return SPH_OK;
+}
 
 // ---------------------------------------------------------------- slab mode (multi-GPU) ----------
 // NCCL is resolved at run time (dlopen) so that the single-GPU library has no link dependency and, in
@@ -584,11 +605,13 @@ int sph_destroy(sph_context *c) {
     drop_graph(c);
     void *ptrs[] = {c->pos_a, c->vel_a, c->pos_s, c->vel_s, c->dp, c->acc, c->nb_count, c->g.key_a, c->g.off_a,
                     c->g.bucket_src, c->g.bucket_id, c->g.key_s, c->g.count, c->g.cell_start, c->g.scan_status,
-                    c->d_stage, c->d_tmp_i32, c->d_tmp_f32, c->d_stats, c->nb.xs, c->nb.ys, c->nb.zs, c->nb.fdat, c->nb.mask, c->nb.words, c->nb.ovf};
+                    c->d_stage, c->d_tmp_i32, c->d_tmp_f32, c->d_stats, c->d_id_error, c->d_hist, c->nb.xs, c->nb.ys, c->nb.zs, c->nb.fdat, c->nb.mask, c->nb.words, c->nb.ovf};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->d_flush) cudaFree(c->d_flush);
     if (c->d_mesh_planes) cudaFree(c->d_mesh_planes);
+    if (c->d_emit_pos) cudaFree(c->d_emit_pos);
+    if (c->d_emit_vel) cudaFree(c->d_emit_vel);
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
         cudaStreamDestroy(c->copy_stream);
@@ -679,6 +702,9 @@ int sph_create(const sph_config *cfg, sph_context **out) {
     CTX_TRY(dalloc(&c->d_tmp_i32, cap));
     CTX_TRY(dalloc(&c->d_tmp_f32, cap * 5));
     CTX_TRY(dalloc(&c->d_stats, (size_t)8));
+    CTX_TRY(dalloc(&c->d_id_error, (size_t)1));
+    CTX_TRY(cudaMemsetAsync(c->d_id_error, 0, sizeof(int), c->stream));
+    CTX_TRY(dalloc(&c->d_hist, (size_t)kHistBins));
     c->stage_cap = std::min<size_t>(cap, (size_t)4 << 20);  // <= 4 Mi records (320 MiB) of AoS staging
     CTX_TRY(dalloc(&c->d_stage, c->stage_cap));
     CTX_TRY(cudaMemsetAsync(c->g.count, 0, c->cells_padded * sizeof(int), c->stream));
@@ -712,7 +738,8 @@ static int upload_range(sph_context *c, const sph_particle *aos, uint32_t first,
         const uint32_t chunk = (uint32_t)std::min<size_t>(count - done, c->stage_cap);
         CUDA_TRY(c, cudaMemcpyAsync(c->d_stage, aos + done, (size_t)chunk * sizeof(sph_particle), cudaMemcpyHostToDevice,
                                     c->stream));
-        launch_aos_to_soa(c->d_stage, c->pos_a + first + done, c->vel_a + first + done, (int)chunk, c->stream);
+        launch_aos_to_soa(c->d_stage, c->pos_a + first + done, c->vel_a + first + done, (int)chunk,
+                          c->slab ? 0xffffffffu : c->cap, c->d_id_error, c->stream);  // slab contexts carry global ids
         c->kernel_launches += 1;
         done += chunk;
         if (done < count) CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // staging buffer is reused
@@ -732,6 +759,7 @@ int sph_upload_particles(sph_context *c, const sph_particle *aos, uint32_t n) {
         c->slab->have_ghosts = false;
     }
     c->s_valid = c->grid_valid = c->a_aligned = c->density_valid = c->forces_valid = false;
+    CUDA_TRY(c, cudaMemsetAsync(c->d_id_error, 0, sizeof(int), c->stream));  // the whole state is replaced
     return upload_range(c, aos, 0, n);
 }
 
@@ -748,16 +776,70 @@ int sph_append_particles(sph_context *c, const sph_particle *aos, uint32_t n_new
     return upload_range(c, aos, first, n_new);
 }
 
+int sph_set_emitter(sph_context *c, const sph_particle *templates, uint32_t n_templates, uint32_t group, uint32_t max_count) {
+    REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    REQUIRE(c, !c->slab, SPH_ERR_STATE, "sph_set_emitter: not available in slab mode");
+    REQUIRE(c, n_templates == 0 || (templates && group > 0 && n_templates % group == 0), SPH_ERR_ARGUMENT,
+            "sph_set_emitter: templates must come in whole groups");
+    REQUIRE(c, max_count <= c->cap, SPH_ERR_ARGUMENT, "sph_set_emitter: max_count exceeds max_particles");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->d_emit_pos) cudaFree(c->d_emit_pos), c->d_emit_pos = nullptr;
+    if (c->d_emit_vel) cudaFree(c->d_emit_vel), c->d_emit_vel = nullptr;
+    c->emit_templates = c->emit_group = c->emit_max = 0;
+    if (n_templates == 0) return SPH_OK;
+    std::vector<float4> pos(n_templates), vel(n_templates);
+    for (uint32_t t = 0; t < n_templates; ++t) {
+        pos[t] = make_float4(templates[t].position[0], templates[t].position[1], templates[t].position[2], 0.f);
+        vel[t] = make_float4(templates[t].velocity[0], templates[t].velocity[1], templates[t].velocity[2], 0.f);
+    }
+    CUDA_TRY(c, dalloc(&c->d_emit_pos, (size_t)n_templates));
+    CUDA_TRY(c, dalloc(&c->d_emit_vel, (size_t)n_templates));
+    CUDA_TRY(c, cudaMemcpy(c->d_emit_pos, pos.data(), n_templates * sizeof(float4), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_emit_vel, vel.data(), n_templates * sizeof(float4), cudaMemcpyHostToDevice));
+    c->emit_templates = n_templates;
+    c->emit_group = group;
+    c->emit_max = max_count;
+    return SPH_OK;
+}
+
+// One emission (the generateParticles() call at the top of step(), src/CBaseParticleSimulator.cpp:120,187-210): group g of
+// the templates is appended while count < max_count - group, ids continue the running count.  Nothing crosses PCIe.
+static uint32_t enqueue_emit(sph_context *c) {
+    if (!c->emit_templates) return 0;
+    uint32_t groups = 0;
+    const uint32_t total = c->emit_templates / c->emit_group;
+    while (groups < total && c->emit_max >= c->emit_group && c->n + groups * c->emit_group < c->emit_max - c->emit_group &&
+           c->n + (groups + 1) * c->emit_group <= c->cap)
+        ++groups;
+    const uint32_t n_new = groups * c->emit_group;
+    if (n_new == 0) return 0;
+    launch_emit(c->d_emit_pos, c->d_emit_vel, (int)n_new, c->pos_a + c->in_off + c->n, c->vel_a + c->in_off + c->n, c->n, c->stream);
+    c->kernel_launches += 1;
+    c->n += n_new;
+    c->s_valid = c->grid_valid = c->a_aligned = c->density_valid = c->forces_valid = false;
+    return n_new;
+}
+
+int sph_emit(sph_context *c, uint32_t *n_emitted) {
+    REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const uint32_t k = enqueue_emit(c);
+    if (n_emitted) *n_emitted = k;
+    return check_launch(c, "emit");
+}
+
 int sph_download_particles(sph_context *c, sph_particle *aos, uint32_t capacity, uint32_t *n_out) {
     REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
     REQUIRE(c, aos && capacity >= c->n, SPH_ERR_ARGUMENT, "sph_download_particles: buffer too small");
     REQUIRE(c, !c->slab, SPH_ERR_STATE, "sph_download_particles: indexed by global id - not available in slab mode (use sph_download_owned)");
     CUDA_TRY(c, cudaSetDevice(c->device));
     if (int rc = drain_async_download(c)) return rc;
+    if (int rc = id_precondition(c, "sph_download_particles")) return rc;
     const bool aux = aux_aligned(c);
     for (uint32_t base = 0; base < c->n;) {
         const uint32_t chunk = (uint32_t)std::min<size_t>(c->n - base, c->stage_cap);
-        launch_soa_to_aos(view_pos(c), view_vel(c), aux ? c->acc : nullptr, aux ? c->dp : nullptr,
+        launch_soa_to_aos(view_pos(c), view_vel(c), aux_acc(c), aux_dp(c),
                           (aux && c->grid_valid) ? c->g.key_s : nullptr, c->d_stage, (int)base, (int)chunk, (int)c->n,
                           c->P, c->stream);
         c->kernel_launches += 1;
@@ -786,7 +868,7 @@ int sph_download_particles_async(sph_context *c, sph_particle *aos, uint32_t cap
     c->copy_n = c->n;
     if (c->n > 0) {
         const bool aux = aux_aligned(c);
-        launch_soa_to_aos(view_pos(c), view_vel(c), aux ? c->acc : nullptr, aux ? c->dp : nullptr,
+        launch_soa_to_aos(view_pos(c), view_vel(c), aux_acc(c), aux_dp(c),
                           (aux && c->grid_valid) ? c->g.key_s : nullptr, c->d_stage, 0, (int)c->n, (int)c->n, c->P, c->stream);
         c->kernel_launches += 1;
     }
@@ -935,7 +1017,36 @@ int sph_step(sph_context *c, int n_steps, double *ms) {
         if (ms) *ms = 0.0;
         return SPH_OK;
     }
-    // Capture the step once the particle count is stable (a fountain still filling changes n every step).
+    // Fountain still filling: every step starts with a device-side emission, the particle count changes, so the steps
+    // are launched directly (fused kernels, no graph, no host transfer) until the emitter has run dry.
+    if (c->emit_templates) {
+        PhaseTimer t(c, ms);
+        int k = 0;
+        for (; k < n_steps; ++k) {
+            if (enqueue_emit(c) == 0 && c->n > 0) break;  // cap reached: the rest runs on the stable-count path below
+            if (c->n == 0) continue;
+            enqueue_step(c);
+            c->last_step_n = c->n;
+        }
+        c->steps += (uint64_t)k;
+        if (k > 0 && c->n > 0) c->s_valid = c->grid_valid = c->density_valid = c->forces_valid = c->a_aligned = true;
+        int rc = check_launch(c, "step (emitting)");
+        if (rc) return rc;
+        if (k == n_steps) return t.finish();
+        double ms_head = 0.0, ms_tail = 0.0;
+        if (ms) {
+            rc = t.finish();
+            if (rc) return rc;
+            ms_head = *ms;
+        }
+        const uint32_t tpl = c->emit_templates;
+        c->emit_templates = 0;  // dry: recurse once into the ordinary path for the remaining steps
+        rc = sph_step(c, n_steps - k, ms ? &ms_tail : nullptr);
+        c->emit_templates = tpl;
+        if (ms) *ms = ms_head + ms_tail;
+        return rc;
+    }
+    // Capture the step once the particle count is stable.
     if (c->opt_use_graph && !c->graph_exec && c->last_step_n == c->n) {
         cudaGraph_t graph = nullptr;
         const uint64_t launches_before = c->kernel_launches;
@@ -1025,6 +1136,7 @@ int sph_download_keys(sph_context *c, int32_t *keys) {
     c->kernel_launches += 1;
     CUDA_TRY(c, cudaMemcpyAsync(keys, c->d_tmp_i32, (size_t)c->n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (int rc = id_precondition(c, "sph_download_keys")) return rc;
     return check_launch(c, "download_keys");
 }
 
@@ -1071,6 +1183,7 @@ int sph_download_density_pressure_accel(sph_context *c, float *density, float *p
     CUDA_TRY(c, cudaMemcpyAsync(pressure, prs, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(accel3, a3, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (int rc = id_precondition(c, "sph_download_density_pressure_accel")) return rc;
     return check_launch(c, "download_density_pressure_accel");
 }
 
@@ -1084,6 +1197,7 @@ int sph_download_neighbours(sph_context *c, int32_t *counts, int32_t *lists, uin
     c->kernel_launches += 1;
     CUDA_TRY(c, cudaMemcpyAsync(counts, c->d_tmp_i32, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (int rc = id_precondition(c, "sph_download_neighbours")) return rc;
     std::vector<long long> offsets(n + 1, 0);
     for (size_t i = 0; i < n; ++i) offsets[i + 1] = offsets[i] + counts[i];
     if (total) *total = (uint64_t)offsets[n];
@@ -1107,6 +1221,43 @@ int sph_download_neighbours(sph_context *c, int32_t *counts, int32_t *lists, uin
     CUDA_TRY(c, e);
     for (size_t i = 0; i < n; ++i) std::sort(lists + offsets[i], lists + offsets[i + 1]);
     return check_launch(c, "download_neighbours");
+}
+
+int sph_download_mask_neighbours(sph_context *c, int32_t *counts, int32_t *lists, uint64_t lists_capacity, uint64_t *total) {
+    REQUIRE(c, c && counts, SPH_ERR_ARGUMENT, "sph_download_mask_neighbours: NULL argument");
+    REQUIRE(c, c->grid_valid && c->density_valid, SPH_ERR_STATE, "sph_download_mask_neighbours: run sph_density_pressure first");
+    REQUIRE(c, use_mask_passes(c), SPH_ERR_STATE, "sph_download_mask_neighbours: the bitmask passes are not in use (variant 0 or a grid narrower than 4 cells)");
+    REQUIRE(c, !c->slab, SPH_ERR_STATE, "sph_download_mask_neighbours: indexed by global id - not available in slab mode");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const size_t n = c->n;
+    launch_mask_lists(c->nb, c->pos_s, c->g.key_s, c->g.cell_start, nullptr, nullptr, c->d_tmp_i32, (int)n, c->P, c->stream);
+    c->kernel_launches += 1;
+    CUDA_TRY(c, cudaMemcpyAsync(counts, c->d_tmp_i32, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (int rc = id_precondition(c, "sph_download_mask_neighbours")) return rc;
+    std::vector<long long> offsets(n + 1, 0);
+    for (size_t i = 0; i < n; ++i) offsets[i + 1] = offsets[i] + counts[i];
+    if (total) *total = (uint64_t)offsets[n];
+    if (!lists) return check_launch(c, "download_mask_neighbours");
+    REQUIRE(c, lists_capacity >= (uint64_t)offsets[n], SPH_ERR_ARGUMENT, "sph_download_mask_neighbours: lists buffer too small");
+    long long *d_off = nullptr;
+    int *d_lists = nullptr;
+    CUDA_TRY(c, dalloc(&d_off, n + 1));
+    cudaError_t e = dalloc(&d_lists, (size_t)offsets[n]);
+    if (e != cudaSuccess) {
+        cudaFree(d_off);
+        CUDA_TRY(c, e);
+    }
+    cudaMemcpyAsync(d_off, offsets.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream);
+    launch_mask_lists(c->nb, c->pos_s, c->g.key_s, c->g.cell_start, d_off, d_lists, nullptr, (int)n, c->P, c->stream);
+    c->kernel_launches += 1;
+    cudaMemcpyAsync(lists, d_lists, (size_t)offsets[n] * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_off);
+    cudaFree(d_lists);
+    CUDA_TRY(c, e);
+    for (size_t i = 0; i < n; ++i) std::sort(lists + offsets[i], lists + offsets[i + 1]);
+    return check_launch(c, "download_mask_neighbours");
 }
 
 // ---------------------------------------------------------------- all-pairs variant
@@ -1157,6 +1308,7 @@ int sph_brute_neighbour_counts(sph_context *c, int32_t *counts) {
     c->kernel_launches += 1;
     CUDA_TRY(c, cudaMemcpyAsync(counts, c->d_tmp_i32, (size_t)c->n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (int rc = id_precondition(c, "sph_brute_neighbour_counts")) return rc;
     return check_launch(c, "brute_neighbour_counts");
 }
 
@@ -1194,6 +1346,40 @@ int sph_stats(sph_context *c, double *out6) {
     return check_launch(c, "stats");
 }
 
+// Exact order statistic of the fill height y + b/2 by two histogram passes: 4096 bins over the box, then 4096 bins
+// inside the bin that holds rank k = floor(q (n - 1)) (the definition oracle_stats uses).  The answer
+// is the centre of a sub-bin of width box_y / 4096^2 — far below fp32 resolution of the coordinate.
+int sph_fill_height_percentile(sph_context *c, double q, double *height) {
+    REQUIRE(c, c && height, SPH_ERR_ARGUMENT, "sph_fill_height_percentile: NULL argument");
+    REQUIRE(c, q >= 0.0 && q <= 1.0, SPH_ERR_ARGUMENT, "sph_fill_height_percentile: q outside [0, 1]");
+    REQUIRE(c, !c->slab, SPH_ERR_STATE, "sph_fill_height_percentile: a global order statistic - not available in slab mode");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    *height = 0.0;
+    if (c->n == 0) return SPH_OK;
+    const uint64_t k = (uint64_t)(q * (double)(c->n - 1));
+    std::vector<unsigned> h(kHistBins);
+    double lo = -(double)c->cfg.box[1] / 2.0, width = (double)c->cfg.box[1] / kHistBins;
+    uint64_t below = 0;  // particles in bins before the selected one
+    for (int pass = 0; pass < 2; ++pass) {
+        launch_hist_y(view_pos(c), (int)c->n, lo, 1.0 / width, pass == 0 ? 1 : 0, c->d_hist, c->stream);
+        c->kernel_launches += 1;
+        CUDA_TRY(c, cudaMemcpyAsync(h.data(), c->d_hist, kHistBins * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        // pass 0 clamps out-of-box particles into the edge bins; pass 1 only counts particles of the selected bin
+        uint64_t run = pass == 0 ? 0 : below;
+        int b = 0;
+        for (; b < kHistBins - 1; ++b) {
+            if (run + h[b] > k) break;
+            run += h[b];
+        }
+        below = run;
+        lo += width * b;
+        if (pass == 0) width /= kHistBins;
+    }
+    *height = lo + 0.5 * width + (double)c->cfg.box[1] / 2.0;
+    return check_launch(c, "fill_height_percentile");
+}
+
 // ---------------------------------------------------------------- options / counters
 int sph_set_option(sph_context *c, const char *name, int value) {
     REQUIRE(c, c && name, SPH_ERR_ARGUMENT, "sph_set_option: NULL argument");
@@ -1220,14 +1406,19 @@ int sph_get_counter(const sph_context *c, const char *name, uint64_t *value) {
     if (k == "kernel_launches") *value = c->kernel_launches;
     else if (k == "graph_launches") *value = c->graph_launches;
     else if (k == "steps") *value = c->steps;
-    else if (k == "overflow_particles") {  // particles of the last density pass whose hit words did not fit
+    else if (k == "overflow_particles" || k == "slab_far_movers") {
+        // overflow_particles: particles of the last density pass whose hit words did not fit;
+        // slab_far_movers: particles the boundary-only exchange would have missed (must stay 0).
+        // Device counters: read on the context's device, ordered behind the work already queued on its streams.
         int v = 0;
-        cudaMemcpy(&v, c->nb.ovf, sizeof(int), cudaMemcpyDeviceToHost);
-        *value = (uint64_t)v;
-    }
-    else if (k == "slab_far_movers") {  // particles the boundary-only exchange would have missed (must stay 0)
-        int v = 0;
-        if (c->slab) cudaMemcpy(&v, c->slab->d_counters + 4, sizeof(int), cudaMemcpyDeviceToHost);
+        const int *src = k == "overflow_particles" ? c->nb.ovf : (c->slab ? c->slab->d_counters + 4 : nullptr);
+        if (src) {
+            if (cudaSetDevice(c->device) != cudaSuccess) return SPH_ERR_CUDA;
+            if (c->slab && c->slab->comm_stream && cudaStreamSynchronize(c->slab->comm_stream) != cudaSuccess) return SPH_ERR_CUDA;
+            if (cudaMemcpyAsync(&v, src, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                cudaStreamSynchronize(c->stream) != cudaSuccess)
+                return SPH_ERR_CUDA;
+        }
         *value = (uint64_t)v;
     }
     else return SPH_ERR_ARGUMENT;
@@ -1353,7 +1544,8 @@ int sph_download_owned(sph_context *c, sph_particle *aos, uint32_t capacity, uin
         const uint32_t chunk = (uint32_t)std::min<size_t>(n - base, c->stage_cap);
         const size_t o = (size_t)off + base;
         launch_soa_to_aos((c->a_aligned || !c->s_valid ? c->pos_a : c->pos_s) + o, (c->a_aligned || !c->s_valid ? c->vel_a : c->vel_s) + o,
-                          aux ? c->acc + o : nullptr, aux ? c->dp + o : nullptr, aux ? c->g.key_s + o : nullptr, c->d_stage,
+                          (aux && c->forces_valid) ? c->acc + o : nullptr, (aux && c->density_valid) ? c->dp + o : nullptr,
+                          aux ? c->g.key_s + o : nullptr, c->d_stage,
                           -1, (int)chunk, (int)chunk, c->P, c->stream);
         c->kernel_launches += 1;
         CUDA_TRY(c, cudaMemcpyAsync(aos + base, c->d_stage, (size_t)chunk * sizeof(sph_particle), cudaMemcpyDeviceToHost,

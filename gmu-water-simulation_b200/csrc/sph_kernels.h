@@ -68,11 +68,16 @@ struct ParticleAoS {  // == sph_particle
     float density, pressure;
     unsigned id, cell_id;
 };
-void launch_aos_to_soa(const ParticleAoS *aos, float4 *pos, float4 *vel, int n, cudaStream_t st);
+// id_error (may be NULL): set to 1 when a record's id is >= id_limit
+void launch_aos_to_soa(const ParticleAoS *aos, float4 *pos, float4 *vel, int n, unsigned id_limit, int *id_error,
+                       cudaStream_t st);
 // id_base >= 0: record of particle `id` goes to aos[id - id_base] (ids outside [id_base, id_base+id_count) are skipped);
 // id_base < 0 : compact mode, particle at index i goes to aos[i] (slab mode: owned sub-range, order = canonical order)
 void launch_soa_to_aos(const float4 *pos, const float4 *vel, const float4 *acc, const float4 *dp, const int *key,
                        ParticleAoS *aos_by_id, int id_base, int id_count, int n, const Params &P, cudaStream_t st);
+// fountain emission on the device: n_new template records appended, ids id_base .. id_base + n_new - 1
+void launch_emit(const float4 *tpl_pos, const float4 *tpl_vel, int n_new, float4 *pos_out, float4 *vel_out, unsigned id_base,
+                 cudaStream_t st);
 // slab mode: append the owned particles lying in the 2+2 layers around each face to the send buffers
 void launch_gather4(const int *src, size_t i0, size_t i1, size_t i2, size_t i3, int *dst, cudaStream_t st);
 void launch_slab_pack(const float4 *pos, const float4 *vel, int n, int z_lo_below, int z_hi_from, float4 *down_pos,
@@ -89,7 +94,14 @@ void launch_extract_ids(const float4 *pos, unsigned *ids, int n, cudaStream_t st
 // neighbour lists: pass 1 counts (by id), pass 2 fills lists at offsets[id] (unsorted; host sorts each list)
 void launch_neighbour_lists(const float4 *pos_s, const int *key_s, const int *cell_start, const long long *offsets_by_id,
                             int *lists, int n, const Params &P, cudaStream_t st);
+// the stored hit words (what the force pass consumes) decoded into id lists; lists == NULL: counts only
+void launch_mask_lists(const NbBuffers &nb, const float4 *pos_s, const int *key_s, const int *cell_start,
+                       const long long *offsets_by_id, int *lists, int *counts_by_id, int n, const Params &P, cudaStream_t st);
 void launch_flush_l2(float4 *buf, size_t count, cudaStream_t st);
 void launch_stats(const float4 *pos, const float4 *vel, int n, double *out8, cudaStream_t st);
+// histogram of floor((y - lo) * inv_width) over kHistBins bins; `clamp` puts out-of-range values into the edge bins,
+// otherwise they are not counted (refinement pass inside one bin)
+constexpr int kHistBins = 4096;
+void launch_hist_y(const float4 *pos, int n, double lo, double inv_width, int clamp, unsigned *hist, cudaStream_t st);
 
 }  // namespace sph

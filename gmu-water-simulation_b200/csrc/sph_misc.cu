@@ -8,7 +8,8 @@ namespace sph {
 // The reference's host mirror m_clParticles is an array of 80-byte CParticle::Physics records
 // (include/CParticle.h:19-43).  It is kept only at the boundary; on the device everything is SoA.
 __global__ void __launch_bounds__(256) k_aos_to_soa(const ParticleAoS *__restrict__ aos, float4 *__restrict__ pos,
-                                                    float4 *__restrict__ vel, int n) {
+                                                    float4 *__restrict__ vel, int n, unsigned id_limit,
+                                                    int *__restrict__ id_error) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 *rec = reinterpret_cast<const float4 *>(aos + i);
@@ -19,11 +20,14 @@ __global__ void __launch_bounds__(256) k_aos_to_soa(const ParticleAoS *__restric
     v.w = 0.0f;
     pos[i] = p;
     vel[i] = v;
+    // precondition of the ABI: ids are unique and < max_particles (by-id read-backs index host arrays with them)
+    if (id_error && __float_as_uint(tail.z) >= id_limit) atomicOr(id_error, 1);
 }
 
-void launch_aos_to_soa(const ParticleAoS *aos, float4 *pos, float4 *vel, int n, cudaStream_t st) {
+void launch_aos_to_soa(const ParticleAoS *aos, float4 *pos, float4 *vel, int n, unsigned id_limit, int *id_error,
+                       cudaStream_t st) {
     if (n <= 0) return;
-    k_aos_to_soa<<<(n + 255) / 256, 256, 0, st>>>(aos, pos, vel, n);
+    k_aos_to_soa<<<(n + 255) / 256, 256, 0, st>>>(aos, pos, vel, n, id_limit, id_error);
 }
 
 __global__ void __launch_bounds__(256) k_soa_to_aos(const float4 *__restrict__ pos, const float4 *__restrict__ vel,
@@ -58,12 +62,31 @@ void launch_soa_to_aos(const float4 *pos, const float4 *vel, const float4 *acc, 
     k_soa_to_aos<<<(n + 255) / 256, 256, 0, st>>>(pos, vel, acc, dp, key, aos_by_id, id_base, id_count, n, P);
 }
 
+// ================================================================= fountain emission
+// generateParticles (src/CBaseParticleSimulator.cpp:187-210) on the device: the records one step appends are fixed
+// templates (nozzle pattern at the box floor, velocity (0, 3.2 b, 0)); only the ids change (the running count).
+__global__ void k_emit(const float4 *__restrict__ tpl_pos, const float4 *__restrict__ tpl_vel, int n_new,
+                       float4 *__restrict__ pos_out, float4 *__restrict__ vel_out, unsigned id_base) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_new) return;
+    float4 p = __ldg(tpl_pos + t);
+    p.w = __uint_as_float(id_base + (unsigned)t);
+    pos_out[t] = p;
+    vel_out[t] = __ldg(tpl_vel + t);
+}
+void launch_emit(const float4 *tpl_pos, const float4 *tpl_vel, int n_new, float4 *pos_out, float4 *vel_out, unsigned id_base,
+                 cudaStream_t st) {
+    if (n_new <= 0) return;
+    k_emit<<<(n_new + 127) / 128, 128, 0, st>>>(tpl_pos, tpl_vel, n_new, pos_out, vel_out, id_base);
+}
+
 // ================================================================= taps
 __global__ void __launch_bounds__(256) k_scatter_by_id_i32(const float4 *__restrict__ pos, const int *__restrict__ src,
                                                            int *__restrict__ dst, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    dst[__float_as_int(__ldg(&pos[i].w))] = src[i];
+    const unsigned id = __float_as_uint(__ldg(&pos[i].w));
+    if (id < (unsigned)n) dst[id] = src[i];  // ids outside [0, n) are skipped (the upload flagged them), never written
 }
 void launch_scatter_by_id_i32(const float4 *pos, const int *src, int *dst_by_id, int n, cudaStream_t st) {
     if (n <= 0) return;
@@ -75,7 +98,8 @@ __global__ void __launch_bounds__(256) k_scatter_cell_ids(const float4 *__restri
                                                           int *__restrict__ dst, int n, const __grid_constant__ Params P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    dst[__float_as_int(__ldg(&pos[i].w))] = coarse_key(__ldg(key + i), P);
+    const unsigned id = __float_as_uint(__ldg(&pos[i].w));
+    if (id < (unsigned)n) dst[id] = coarse_key(__ldg(key + i), P);
 }
 void launch_scatter_cell_ids(const float4 *pos, const int *key, int *dst_by_id, int n, const Params &P, cudaStream_t st) {
     if (n <= 0) return;
@@ -115,7 +139,8 @@ __global__ void __launch_bounds__(256) k_scatter_dpa(const float4 *__restrict__ 
                                                      float *__restrict__ prs, float *__restrict__ acc3, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int id = __float_as_int(__ldg(&pos[i].w));
+    const unsigned id = __float_as_uint(__ldg(&pos[i].w));
+    if (id >= (unsigned)n) return;
     const float4 d = __ldg(dp + i), a = __ldg(acc + i);
     rho[id] = d.x;
     prs[id] = d.y;
@@ -146,7 +171,8 @@ __global__ void __launch_bounds__(128) k_neighbour_lists(const float4 *__restric
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 pi = __ldg(pos + i);
-    long long w = offsets_by_id[__float_as_int(pi.w)];
+    if (__float_as_uint(pi.w) >= (unsigned)n) return;
+    long long w = offsets_by_id[__float_as_uint(pi.w)];
     const float h2 = P.h2;
     for_each_row(__ldg(key + i), cell_start, P, [&](int a, int b) {
         for (int j = a; j < b; ++j) {
@@ -356,6 +382,33 @@ __global__ void __launch_bounds__(256) k_stats(const float4 *__restrict__ pos, c
         for (int k = 0; k < 5; ++k) atomicAdd(out + k, s[k]);
         atomicMax(reinterpret_cast<unsigned *>(out + 5), ymax);
     }
+}
+
+// fill-height histogram: bin = floor((y - lo) * inv_width) in fp64 (the same expression in both passes, so a
+// particle counted in bin b of the coarse pass falls inside [0, kHistBins) of the refinement of bin b)
+__global__ void __launch_bounds__(256) k_hist_y(const float4 *__restrict__ pos, int n, double lo, double inv_width,
+                                                int clamp, unsigned *__restrict__ hist) {
+    __shared__ unsigned s_hist[kHistBins];
+    for (int b = threadIdx.x; b < kHistBins; b += blockDim.x) s_hist[b] = 0u;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double t = ((double)__ldg(&pos[i].y) - lo) * inv_width;
+        // NaN compares false everywhere: a non-finite particle lands in bin 0, like the host-side nth_element puts it first
+        int b = t >= 0.0 ? (t < (double)kHistBins ? (int)t : kHistBins) : -1;
+        if (clamp) b = min(max(b, 0), kHistBins - 1);  // coarse pass: out-of-box particles go into the edge bins
+        if (b >= 0 && b < kHistBins) atomicAdd(&s_hist[b], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kHistBins; b += blockDim.x)
+        if (s_hist[b]) atomicAdd(hist + b, s_hist[b]);
+}
+
+void launch_hist_y(const float4 *pos, int n, double lo, double inv_width, int clamp, unsigned *hist, cudaStream_t st) {
+    cudaMemsetAsync(hist, 0, kHistBins * sizeof(unsigned), st);
+    if (n <= 0) return;
+    int blocks = (n + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    k_hist_y<<<blocks, 256, 0, st>>>(pos, n, lo, inv_width, clamp, hist);
 }
 
 void launch_stats(const float4 *pos, const float4 *vel, int n, double *out8, cudaStream_t st) {

@@ -226,7 +226,14 @@ __global__ void __launch_bounds__(128, 8) k_density_mask(const float *__restrict
     float s0, s1, s2, s3;
     upk(sum_a, s0, s1);
     upk(sum_b, s2, s3);
-    const float sum = ((s0 + s1) + (s2 + s3)) - stray_sum;
+    float sum = ((s0 + s1) + (s2 + s3)) - stray_sum;
+    if (!(px < 1.0e17f)) {
+        // a particle with a non-finite coordinate (sentinel in xs/ys/zs): in the reference every comparison with NaN
+        // is false, so it has no neighbours at all, not even itself -> density 0 (src/CCPUParticleSimulator.cpp:122-127)
+        sum = 0.0f;
+        cnt = 0;
+        widx = 0;
+    }
     // Wpoly6 summed, then rho *= mass; p = k (rho - rho0)   (src/CCPUParticleSimulator.cpp:9-15,133-134)
     float rho = sum * P.poly6_f;
     rho *= P.mass;
@@ -298,7 +305,9 @@ __device__ __forceinline__ void force_epilogue(const int i, const ForceSum &f, c
                                                int *__restrict__ far_movers, const Params &P) {
     float4 a = force_result(f, __ldg(&dp[i].x), P);
     if (FUSED) {
-        const float4 p = make_float4(pi.x, pi.y, pi.z, __ldg(&pos_s[i].w));  // .w carries the particle id
+        // the particle's real position: pos_s, not its candidate record (a non-finite particle carries the far-away
+        // sentinel there and must stay non-finite, like in the phase path and in the reference); .w = particle id
+        const float4 p = __ldg(pos_s + i);
         const float4 v = make_float4(vi.x, vi.y, vi.z, 0.0f);
         float4 np, nv;
         walls_and_integrate(p, v, a, np, nv, P);
@@ -396,6 +405,58 @@ __global__ void __launch_bounds__(128) k_forces_mask(const float4 *__restrict__ 
         pair_term(f, pi, vi, pj, vj, j == i, P);
     }
     force_epilogue<FUSED>(i, f, pi, vi, dp, pos_s, acc, pos_out, vel_out, key, far_movers, P);
+}
+
+// ================================================================= validation tap: the stored hit words as id lists
+// Decodes exactly what k_forces_mask consumes — the words {bits, j0 + 31} the density pass stored — into neighbour id
+// lists (self included, like the reference's predicate).  Particles whose words overflowed are enumerated the way
+// k_forces_overflow walks them.  lists[offsets_by_id[id] ...] receives the ids in walk order (the host sorts).
+__global__ void __launch_bounds__(128) k_mask_lists(const float4 *__restrict__ pos_s, const float *__restrict__ xs,
+                                                    const float *__restrict__ ys, const float *__restrict__ zs,
+                                                    const uint2 *__restrict__ mask, const int *__restrict__ nb_words,
+                                                    const int *__restrict__ key, const int *__restrict__ cell_start,
+                                                    const long long *__restrict__ offsets_by_id, int *__restrict__ lists,
+                                                    int *__restrict__ counts_by_id, int n, const __grid_constant__ Params P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned id = __float_as_uint(__ldg(&pos_s[i].w));
+    if (id >= (unsigned)n) return;
+    long long w = lists ? offsets_by_id[id] : 0;
+    int cnt = 0;
+    const int nw = __ldg(nb_words + i);
+    if (nw <= kMaskWords) {
+        const uint2 *const wbase = mask + ((size_t)(i >> 5) * kMaskWords) * 32 + (i & 31);
+        for (int k = 0; k < nw; ++k) {
+            const uint2 word = __ldg(wbase + k * 32);
+            unsigned m = word.x;
+            while (m) {
+                const int msb = 31 - __clz(m);
+                m &= ~(1u << msb);
+                const int j = (int)word.y - msb;
+                if (lists) lists[w++] = __float_as_int(__ldg(&pos_s[j].w));
+                ++cnt;
+            }
+        }
+    } else {
+        const float px = __ldg(xs + i), py = __ldg(ys + i), pz = __ldg(zs + i);
+        for_each_row(__ldg(key + i), cell_start, P, [&](int a, int b) {
+            for (int j = a; j < b; ++j) {
+                const float r2 = r2_exact(px - __ldg(xs + j), py - __ldg(ys + j), pz - __ldg(zs + j));
+                if (P.h2 - r2 >= 0.0f) {
+                    if (lists) lists[w++] = __float_as_int(__ldg(&pos_s[j].w));
+                    ++cnt;
+                }
+            }
+        });
+    }
+    if (counts_by_id) counts_by_id[id] = cnt;
+}
+
+void launch_mask_lists(const NbBuffers &nb, const float4 *pos_s, const int *key_s, const int *cell_start,
+                       const long long *offsets_by_id, int *lists, int *counts_by_id, int n, const Params &P, cudaStream_t st) {
+    if (n <= 0) return;
+    k_mask_lists<<<(n + 127) / 128, 128, 0, st>>>(pos_s, nb.xs, nb.ys, nb.zs, nb.mask, nb.words, key_s, cell_start, offsets_by_id,
+                                                  lists, counts_by_id, n, P);
 }
 
 void launch_forces_mask(const NbBuffers &nb, const float4 *dp, const int *nb_count, const int *key_s, const int *cell_start,

@@ -101,12 +101,25 @@ int sph_destroy(sph_context *ctx);
 const char *sph_last_error(const sph_context *ctx); /* ctx may be NULL: error of the last failed create/enumeration */
 
 /* ---- state (≙ enqueueWrite/enqueueRead, include/CLWrapper.h:66-67) ---- */
+/* Particle ids (sph_particle.id) must be unique and < max_particles; the read-backs "indexed by particle id" below
+ * write host slot [id], so to fill every slot the ids must be a permutation of 0..n-1 — what setupScene /
+ * generateParticles produce (src/CBaseParticleSimulator.cpp:69).  An id >= max_particles is detected on the device at
+ * upload; the next by-id read-back then fails with SPH_ERR_ARGUMENT instead of writing out of bounds, and ids in
+ * [n, max_particles) are skipped.  (Slab contexts carry global ids and only offer sph_download_owned.) */
 /* Replace the device state with n particles from the 80-byte AoS host mirror (m_clParticles).  From a page-locked
  * buffer (sph_pin_host_buffer) the copy is asynchronous on the context's stream: leave the records alone until
  * the next synchronising call (a timed phase, sph_download_particles, sph_synchronize). */
 int sph_upload_particles(sph_context *ctx, const sph_particle *aos, uint32_t n);
 /* Fountain emission (src/CBaseParticleSimulator.cpp:187-210): append n_new particles. */
 int sph_append_particles(sph_context *ctx, const sph_particle *aos, uint32_t n_new);
+/* The same emission on the device, so that a filling fountain needs no host transfer per step: templates = the
+ * records ONE step appends (position, velocity; n_templates = group * nozzles, the reference has one nozzle of
+ * group = 7), max_count = m_maxParticlesCount.  With an emitter set, every step of sph_step() starts with
+ * sph_emit(): template group g is appended while count < max_count - group (the reference's test, :191), ids
+ * continue the running count.  n_templates = 0 removes the emitter.  A caller that mirrors the particles on the
+ * host applies the same rule there (CBaseParticleSimulator::generateParticles). */
+int sph_set_emitter(sph_context *ctx, const sph_particle *templates, uint32_t n_templates, uint32_t group, uint32_t max_count);
+int sph_emit(sph_context *ctx, uint32_t *n_emitted); /* one emission now; n_emitted may be NULL */
 /* Read back on demand into aos[id] (the host mirror is indexed by id); capacity in records. */
 int sph_download_particles(sph_context *ctx, sph_particle *aos, uint32_t capacity, uint32_t *n_out);
 /* Viewer bridge (≙ the read-back + updatePosition/updateVelocity loop, src/CGPUBaseParticleSimulator.cpp:84-91, which
@@ -156,6 +169,11 @@ int sph_download_density_pressure_accel(sph_context *ctx, float *density, float 
  * concatenated ascending id lists, particle 0 first; *total = sum(counts) */
 int sph_download_neighbours(sph_context *ctx, int32_t *counts, int32_t *lists, uint64_t lists_capacity, uint64_t *total);
 
+/* The same sets DECODED FROM THE PRODUCTION HIT WORDS: what the density pass stored and the force pass consumes
+ * (bit words per particle plus the overflow list), not a re-evaluation of the predicate.  Same output convention.
+ * SPH_ERR_STATE when the bitmask passes are not in use (option neighbour_variant 0, or a grid narrower than 4 cells). */
+int sph_download_mask_neighbours(sph_context *ctx, int32_t *counts, int32_t *lists, uint64_t lists_capacity, uint64_t *total);
+
 /* ---- all-pairs variant (CGPUBruteParticleSimulator semantics, resources/kernels/sph_brute.cl) ---- */
 int sph_brute_density_pressure(sph_context *ctx, double *ms);
 int sph_brute_forces(sph_context *ctx, double *ms);
@@ -163,6 +181,10 @@ int sph_brute_neighbour_counts(sph_context *ctx, int32_t *counts);
 
 /* ---- rollout statistics on the device: out[0]=KE, out[1..3]=COM, out[4]=max(y)+b/2, out[5]=mean speed ---- */
 int sph_stats(sph_context *ctx, double *out6);
+
+/* q-th order statistic of the fill height y + b/2 over all particles: the element of rank floor(q (n - 1)), exact to
+ * box_y / 4096^2 (two histogram passes on the device).  q = 0.95 is the robust fill height of SURVEY.md §8c. */
+int sph_fill_height_percentile(sph_context *ctx, double q, double *height);
 
 /* ---- tuning / introspection ---- */
 int sph_set_option(sph_context *ctx, const char *name, int value);

@@ -36,6 +36,8 @@ int gmu_sim_set_mirror_stride(gmu_sim *s, int stride);              /* download 
 int gmu_sim_sync_host(gmu_sim *s);                                 /* device -> host mirror, blocking, current state */
 int gmu_sim_wait_host(gmu_sim *s);                                 /* mode 3: complete the read-back in flight */
 int gmu_sim_set_gravity(gmu_sim *s, float gx, float gy, float gz); /* setGravityVector */
+int gmu_sim_get_gravity(gmu_sim *s, float *out3);                  /* the simulator's gravity member */
+int gmu_sim_is_running(gmu_sim *s);                                /* isRunning(): the timer is active (start/toggleSimulation) */
 int gmu_sim_key(gmu_sim *s, int qt_key);                           /* onKeyPressed */
 /* collision mesh for CCollisionGeometry::inverseBounce: n faces x 12 floats (normal, v0, v1, v2); 0 clears it */
 int gmu_sim_set_collision_faces(gmu_sim *s, const float *faces12, int n_faces);
@@ -49,7 +51,15 @@ sph_context *gmu_sim_context(gmu_sim *s);                          /* the simula
 const char *gmu_sim_device_name(gmu_sim *s);                       /* getSelectedDevice() */
 uint64_t gmu_sim_event_count(gmu_sim *s);
 uint64_t gmu_sim_get_events(gmu_sim *s, double *out7, uint64_t max_events);
+int gmu_sim_push_event(gmu_sim *s, const double *ev7);            /* append one record (same 7 doubles) to `events` */
+/* MainWindow::exportLogs (src/mainwindow.cpp:310-368), byte for byte: appends "<Scenario>_<box>.csv" and
+ * "<Scenario>_<box>_detail.csv" in dir; sim_name is the simulation-type combo text ("CUDA Grid") */
 int gmu_sim_export_logs(gmu_sim *s, const char *dir, const char *sim_name);
+/* eSimulationType (include/mainwindow.h:60-63) with the CUDA types appended: "GPU Grid" 0, "GPU Brute Force" 1,
+ * "CPU Grid" 2, "CUDA Grid" 3, "CUDA Brute Force" 4; -1 for an unknown text */
+int gmu_sim_type_from_name(const char *combo_text);
+/* createSimulator(type, ...) (src/mainwindow.cpp:171-201); NULL + gmu_sim_last_error() for the types not built here */
+gmu_sim *gmu_sim_create_by_type(int type, float box_x, float box_y, float box_z, int device, int scenario);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,19 @@ def check_acc(ref, scale, got):
     assert np.all(err <= tol), f"worst acc error/tol = {(err / tol).max():.3f}"
 
 
+def assert_neighbour_sets(ctx, oc, ol, variant=1):
+    """Neighbour sets against the oracle's (src/CCPUParticleSimulator.cpp:122-127), exact.  The sets that matter are
+    the ones the production force pass consumes: the hit words stored by k_density_mask (+ the overflow list), decoded
+    by sph_download_mask_neighbours.  The walk of the separate validation kernel is kept as a cross-check."""
+    if variant == 1 and ctx.uses_mask_passes:
+        mc, ml = ctx.neighbours(source="mask")
+        assert np.array_equal(mc, oc), "production hit mask: neighbour counts differ from the oracle"
+        assert np.array_equal(ml, ol), "production hit mask: neighbour sets differ from the oracle"
+    gc, gl = ctx.neighbours()
+    assert np.array_equal(gc, oc)
+    assert np.array_equal(gl, ol)
+
+
 def phase_parity(gws, o, box, variant=1):
     """One step of both implementations from the oracle's current state, checked phase by phase."""
     pos, vel = o.pos, o.vel
@@ -69,9 +82,7 @@ def phase_parity(gws, o, box, variant=1):
     rho, prs, _ = ctx.density_pressure_accel()
     check_density(o, rho, prs)
     oc, ol = o.neighbours()
-    gc, gl = ctx.neighbours()
-    assert np.array_equal(gc, oc)
-    assert np.array_equal(gl, ol)
+    assert_neighbour_sets(ctx, oc, ol, variant)
     # ---- forces (SPH part), then walls + integration
     o.update_forces()
     ctx.forces()
@@ -136,6 +147,48 @@ def test_phase_parity_golden_fixture(gws):
     rho, prs, acc = ctx.density_pressure_accel()
     assert np.all(np.abs(rho - g["density"]) <= RTOL * g["density"])
     check_acc(g["acc_sph"], g["acc_scale"], acc)
+
+
+@pytest.mark.parametrize("name", ["ref_dam_break_0p4", "ref_dam_break_0p9", "ref_fountain_0p4"])
+def test_parity_against_reference_golden(gws, name):
+    """Vectors written by the REFERENCE'S OWN code (oracle/_ref, tests/golden/make_ref_golden.py): from the stored
+    state before step k, one device step must give the reference's grid exactly and its density / pressure /
+    acceleration / new positions within the north-star tolerance.  No oracle run on the value side; the oracle only
+    supplies the conditioning scale of the acceleration tolerance."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    box = float(g["box"])
+    for k in [int(v) for v in g["steps"]]:
+        pos, vel = g[f"s{k}_pos_before"], g[f"s{k}_vel_before"]
+        n_after = len(g[f"s{k}_pos"])
+        ctx = gws.SphContext(box, max(n_after, 1))
+        ctx.upload(gws.particles_from_arrays(pos, vel))
+        if n_after > len(pos):                           # fountain: this step's emission (closed form, :191-206)
+            hp, h4, y0 = np.float32(0.0457) / np.float32(2), np.float32(0.0457) / np.float32(4), -np.float32(box) / np.float32(2)
+            e = np.array([[0, y0, 0], [-hp, y0, 0], [hp, y0, 0], [-h4, y0, -hp], [h4, y0, -hp], [-h4, y0, hp], [h4, y0, hp]], dtype=np.float32)
+            ev = np.tile(np.array([[0, np.float32(box) * np.float32(3.2), 0]], dtype=np.float32), (7, 1))
+            ctx.append(gws.particles_from_arrays(e, ev, ids=np.arange(len(pos), len(pos) + 7)))
+            pos, vel = np.vstack([pos, e]), np.vstack([vel, ev])
+        assert ctx.n == n_after
+        ctx.update_grid(); ctx.density_pressure(); ctx.forces()
+        cs_ref, ids_ref = g[f"s{k}_cell_start"], g[f"s{k}_ids"]
+        assert np.array_equal(ctx.cell_start(), cs_ref)
+        perm = ctx.permutation().astype(np.int32)
+        # the reference's intra-cell order is its swap-and-pop history; membership per cell must be identical
+        cell_of_slot = np.repeat(np.arange(len(cs_ref) - 1), np.diff(cs_ref))
+        ref_sorted = ids_ref[np.lexsort((ids_ref, cell_of_slot))]
+        assert np.array_equal(perm, ref_sorted)
+        rho, prs, acc_sph = ctx.density_pressure_accel()
+        rho_ref, prs_ref = g[f"s{k}_density"], g[f"s{k}_pressure"]
+        assert np.all(np.abs(rho - rho_ref) <= RTOL * np.abs(rho_ref))
+        assert np.all(np.abs(prs - prs_ref) <= RTOL * np.maximum(np.abs(prs_ref), 3.0 * rho_ref))
+        ctx.integrate()
+        _, _, acc = ctx.density_pressure_accel()
+        o = Oracle(box).set_state(pos, vel)
+        o.update_grid(); o.update_density_pressure(); o.update_forces()
+        check_acc(g[f"s{k}_acc"], o.acc_scale, acc)
+        rec = ctx.download()
+        assert np.all(np.abs(rec["position"][:, :3] - g[f"s{k}_pos"]) <= pos_tolerance(o))
+        ctx.close()
 
 
 def test_rollout_with_resync(gws):
@@ -232,6 +285,84 @@ def test_fountain_through_simulator(gws):
     assert abs(ke_g / o.stats()["ke"] - 1) <= 0.05
 
 
+def test_fountain_step_many_emits_on_the_device_bitwise(gws):
+    """stepMany on a filling fountain: device-side emission (sph_set_emitter / k_emit) + the fused step, no per-step
+    upload and no phase path — bit for bit what step() (host emission + append + phases) produces, through the cap."""
+    box = 0.3   # max 784 particles: the emitter runs dry after 111 steps
+    a = gws.Simulator("cuda", box, scenario=gws.FOUNTAIN).setup_scene()
+    b = gws.Simulator("cuda", box, scenario=gws.FOUNTAIN).setup_scene()
+    a.step(130)
+    b.step_many(60)
+    b.step_many(70)
+    assert a.n == b.n == 7 * 111 and a.iteration == b.iteration == 130
+    assert b.context().counter("graph_launches") > 0        # once the count is stable the graph path takes over
+    a.sync_host(); b.sync_host()
+    ha, hb = a.host_particles(), b.host_particles()
+    for f in ("position", "velocity", "acceleration", "density", "pressure", "id", "cell_id"):
+        assert np.array_equal(ha[f].view(np.uint32), hb[f].view(np.uint32)), f
+    # mixing the two entry points keeps host and device counts in lock-step
+    c = gws.Simulator("cuda", box, scenario=gws.FOUNTAIN).setup_scene()
+    c.step(3); c.step_many(5); c.step(2); c.step_many(120)
+    c.sync_host()
+    assert np.array_equal(c.host_particles()["position"].view(np.uint32), ha["position"].view(np.uint32))
+
+
+def test_fountain_config3_at_size_against_oracle(gws):
+    """BASELINE configs[3]: fountain, box 2.28 (max 250 000 particles), 64 nozzles (emission multiplier), run on the
+    device until more than 100 000 particles are in flight, then ONE step of both implementations from that state:
+    keys, cell ranges, permutation, neighbour sets (production mask) exact; density, pressure, acceleration within
+    rel 1e-5; positions within the acceleration tolerance."""
+    box = 2.28
+    sim = gws.Simulator("cuda", box, scenario=gws.FOUNTAIN).setup_scene()
+    sim.set_emission_multiplier(64)
+    assert sim.max_count == 250000
+    sim.step_many(230)                                   # 64 * 7 * 230 = 103 040 particles, no host transfer
+    assert sim.n == 64 * 7 * 230
+    sim.sync_host()
+    hp = sim.host_particles()
+    assert np.array_equal(hp["id"], np.arange(sim.n, dtype=np.uint32)) and np.isfinite(hp["position"]).all()
+    pos, vel = hp["position"][:, :3].copy(), hp["velocity"][:, :3].copy()
+    o = Oracle(box, FOUNTAIN).set_state(pos, vel)
+    ctx = make_ctx(gws, box, pos, vel, cap=sim.n)
+    o.update_grid(); ctx.update_grid()
+    assert np.array_equal(ctx.keys(), o.keys())
+    cs, perm = o.cells()
+    assert np.array_equal(ctx.cell_start(), cs) and np.array_equal(ctx.permutation().astype(np.int32), perm)
+    o.update_density_pressure(); ctx.density_pressure()
+    oc, ol = o.neighbours()
+    assert_neighbour_sets(ctx, oc, ol)
+    rho, prs, _ = ctx.density_pressure_accel()
+    check_density(o, rho, prs)
+    o.update_forces(); ctx.forces()
+    check_acc(o.acc_sph, o.acc_scale, ctx.density_pressure_accel()[2])
+    ctx.integrate()
+    check_acc(o.acc, o.acc_scale, ctx.density_pressure_accel()[2])
+    rec = ctx.download()
+    tol = pos_tolerance(o)
+    o.integrate()
+    assert np.all(np.abs(rec["position"][:, :3] - o.pos) <= tol)
+    # and the next emission continues the ids on the device
+    sim.step_many(1)
+    assert sim.n == 64 * 7 * 231
+
+
+def test_step_many_keeps_the_mirror_modes(gws):
+    """stepMany() in a non-resident mirror mode refreshes the host mirror after the batch, and in
+    RoundTrip the (canonical) host vector goes up first — a following step() must not rewind the simulation."""
+    box = 0.4
+    o = Oracle(box).setup_scene()
+    sim = gws.Simulator("cuda", box).setup_scene()
+    sim.set_mirror_mode(2)
+    sim.step_many(6); o.step(6)
+    assert np.abs(sim.host_particles()["position"][:, :3] - o.pos).max() <= 1e-4 * 0.0457
+    sim.step(2); o.step(2)                               # uploads the mirror: it must be the state after 6 steps
+    assert np.abs(sim.host_particles()["position"][:, :3] - o.pos).max() <= 1e-4 * 0.0457
+    sim.set_mirror_mode(1)
+    sim.step_many(4); o.step(4)
+    assert np.abs(sim.host_particles()["position"][:, :3] - o.pos).max() <= 2e-4 * 0.0457
+    assert sim.iteration == 12
+
+
 def test_simulator_phase_path_and_mirror_modes(gws):
     box = 0.4
     o = Oracle(box).setup_scene()
@@ -310,8 +441,11 @@ def test_dense_cell_overflow_path(gws, variant, n_clump):
     ctx = make_ctx(gws, 0.4, pos, np.zeros_like(pos), variant=variant)
     o.update_grid(); o.update_density_pressure(); o.update_forces()
     ctx.update_grid(); ctx.density_pressure(); ctx.forces()
-    oc, ol = o.neighbours(); gc, gl = ctx.neighbours()
-    assert oc.max() > 100 and np.array_equal(gc, oc) and np.array_equal(gl, ol)
+    oc, ol = o.neighbours()
+    assert oc.max() > 100
+    assert_neighbour_sets(ctx, oc, ol, variant)
+    if variant == 1:
+        assert (ctx.counter("overflow_particles") > 0) == (n_clump > 1000)  # 1500: the overflow list is what gets decoded
     rho, prs, acc = ctx.density_pressure_accel()
     check_density(o, rho, prs)
     check_acc(o.acc_sph, o.acc_scale, acc)
@@ -349,15 +483,16 @@ def test_full_size_properties_1m(gws):
 def test_rollout_statistics_1000_steps(gws):
     """BASELINE north_star: long rollouts are chaotic, so 1000 steps are compared statistically.  Definitions of
     SURVEY.md §8c, sampled every 10 steps (eventLoggerStride): kinetic energy 0.5 m sum|v|^2, centre of mass,
-    fill height max(y)+b/2.  Stated tolerances: COM within 0.25 h per axis at every sample, fill height (a max over
-    particles, i.e. one splashing particle) within 2 h, KE within 2 % of the run's peak KE at every sample and
+    fill height max(y)+b/2 and its robust form, the 95th percentile of y+b/2.  Stated tolerances: COM within 0.25 h per
+    axis at every sample, fill height (a max over particles, i.e. one splashing particle) within 2 h, its 95th
+    percentile within 0.25 h, KE within 2 % of the run's peak KE at every sample and
     within 5 % relative during the collapse (first 50 steps; afterwards KE decays by five orders of magnitude and
     the two chaotic trajectories only agree in the absolute sense).  Measured on B200: 0.05 h, 1.1 h, 0.6 %, 2 %."""
     box, h = 0.4, 0.0457
     o = Oracle(box).setup_scene()
     sim = gws.Simulator("cuda", box).setup_scene()
     ctx = sim.context()
-    ke_o, ke_g, com_err, fill_err = [], [], [], []
+    ke_o, ke_g, com_err, fill_err, fill95_err = [], [], [], [], []
     for _ in range(100):
         o.step(10)
         sim.step_many(10)
@@ -365,9 +500,11 @@ def test_rollout_statistics_1000_steps(gws):
         ke_o.append(so["ke"]); ke_g.append(sg["ke"])
         com_err.append(np.abs(so["com"] - sg["com"]).max())
         fill_err.append(abs(so["fill"] - sg["fill"]))
+        fill95_err.append(abs(so["fill95"] - ctx.fill_height_percentile(0.95)))
     ke_o, ke_g = np.array(ke_o), np.array(ke_g)
     assert max(com_err) <= 0.25 * h, max(com_err)
     assert max(fill_err) <= 2.0 * h, max(fill_err)
+    assert max(fill95_err) <= 0.25 * h, max(fill95_err)
     assert np.abs(ke_g - ke_o).max() <= 0.02 * ke_o.max()
     assert np.all(np.abs(ke_g[:5] / ke_o[:5] - 1) <= 0.05)
     assert np.isfinite(ke_g).all() and sim.iteration == 1000
@@ -421,8 +558,8 @@ def test_random_states_with_awkward_particles(gws, seed, n, box):
     cs, perm = o.cells()
     assert np.array_equal(ctx.cell_start(), cs) and np.array_equal(ctx.permutation().astype(np.int32), perm)
     o.update_density_pressure(); ctx.density_pressure()
-    oc, ol = o.neighbours(); gc, gl = ctx.neighbours()
-    assert np.array_equal(gc, oc) and np.array_equal(gl, ol)
+    oc, ol = o.neighbours()
+    assert_neighbour_sets(ctx, oc, ol)
     rho, prs, _ = ctx.density_pressure_accel()
     check_density(o, rho, prs)
     o.update_forces(); ctx.forces()
@@ -476,6 +613,56 @@ def test_non_finite_particle_stays_confined(gws, variant):
     o.update_forces(); ctx.forces(); ctx.integrate()
     rec = ctx.download()
     assert np.isfinite(rec["position"][others, :3]).all() and np.isfinite(rec["acceleration"][others, :3]).all()
+    # the reference leaves such a particle non-finite for good (NaN + anything = NaN): so do the phase path and the
+    # FUSED whole-step path (sph_step), bit for bit alike for every other particle
+    assert np.isnan(rec["position"][bad, 0])
+    fused = make_ctx(gws, 0.4, pos, vel, variant=variant)
+    fused.step(1)
+    rf = fused.download()
+    assert np.isnan(rf["position"][bad, 0]) and np.isfinite(rf["position"][others, :3]).all()
+    for f in ("position", "velocity", "acceleration", "density"):
+        assert np.array_equal(rec[f][others].view(np.uint32), rf[f][others].view(np.uint32)), f
+    fused.step(3)
+    rf = fused.download()
+    assert np.isnan(rf["position"][bad, 0]) and np.isfinite(rf["position"][others, :3]).all()
+
+
+def test_exact_percentile_of_fill_height(gws):
+    """sph_fill_height_percentile: the element of rank floor(q (n - 1)) of y + b/2 (oracle_stats' definition)."""
+    o = state_after(0.9, 40)
+    ctx = make_ctx(gws, 0.9, o.pos, o.vel)
+    y = np.sort(o.pos[:, 1].astype(np.float64)) + np.float32(0.9) / 2.0
+    for q in (0.0, 0.05, 0.5, 0.95, 1.0):
+        want = y[int(q * (o.n - 1))]
+        assert abs(ctx.fill_height_percentile(q) - want) <= 1e-6, q
+    assert abs(ctx.fill_height_percentile(0.95) - o.stats()["fill95"]) <= 1e-6
+
+
+def test_particle_id_precondition_is_checked(gws):
+    """by-id read-backs index host arrays with the particle ids.  An id >= max_particles must never be
+    written through; the next by-id read-back reports it.  Ids in [n, max_particles) are skipped, not written."""
+    o = state_after(0.4, 3)
+    n = o.n
+    ctx = gws.SphContext(0.4, n + 8)
+    ids = np.arange(n, dtype=np.uint32)
+    ids[5] = 4_000_000_000
+    ctx.upload(gws.particles_from_arrays(o.pos, o.vel, ids=ids))
+    ctx.update_grid(); ctx.density_pressure()
+    with pytest.raises(gws.SphError, match="max_particles"):
+        ctx.keys()
+    with pytest.raises(gws.SphError, match="max_particles"):
+        ctx.neighbours(lists=False)
+    with pytest.raises(gws.SphError, match="max_particles"):
+        ctx.download()
+    ids[5] = n + 3                                        # inside the capacity but not a permutation of 0..n-1
+    ctx.upload(gws.particles_from_arrays(o.pos, o.vel, ids=ids))   # a full upload re-arms the check
+    ctx.update_grid(); ctx.density_pressure()
+    keys = ctx.keys()
+    ref = make_ctx(gws, 0.4, o.pos, o.vel)
+    ref.update_grid()
+    good = np.arange(n) != 5
+    assert np.array_equal(keys[good], ref.keys()[good])
+    ctx.step(2)                                           # the simulation itself does not depend on the id values
 
 
 def test_full_size_parity_against_oracle_1m(gws):
@@ -497,9 +684,12 @@ def test_full_size_parity_against_oracle_1m(gws):
     assert np.array_equal(ctx.cell_start(), cs)
     assert np.array_equal(ctx.permutation().astype(np.int32), perm)
     o.update_density_pressure(); ctx.density_pressure()
-    oc, _ = o.neighbours(lists=False)
+    oc, ol = o.neighbours()                     # ~6.7e7 ids
     gc, _ = ctx.neighbours(lists=False)
     assert np.array_equal(gc, oc) and oc.mean() > 30
+    mc, ml = ctx.neighbours(source="mask")      # the production hit words at full size, as sets
+    assert np.array_equal(mc, oc) and np.array_equal(ml, ol)
+    del ol, ml
     rho, prs, _ = ctx.density_pressure_accel()
     check_density(o, rho, prs)
     o.update_forces(); ctx.forces()
