@@ -16,6 +16,7 @@ from .binding import (  # noqa: F401
     SphContext,
     SphError,
     build,
+    comm_local_id,
     comm_unique_id,
     simulation_type,
     slab_plan,

@@ -8,7 +8,8 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-_CUDA_SO = os.path.join(_PKG, "libsph_cuda.so")
+# SPH_CUDA_SO: development switch for A/B runs of two builds of the kernel library (tools/kernel_probe.py)
+_CUDA_SO = os.environ.get("SPH_CUDA_SO") or os.path.join(_PKG, "libsph_cuda.so")
 _HOST_SO = os.path.join(_PKG, "libsph_host.so")
 
 DAM_BREAK, FOUNTAIN = 0, 1
@@ -130,6 +131,7 @@ def cuda_lib():
             "sph_set_option": (i32, [vp, C.c_char_p, i32]),
             "sph_get_counter": (i32, [vp, C.c_char_p, P(u64)]),
             "sph_comm_unique_id": (i32, [vp]),
+            "sph_comm_local_id": (i32, [i32, vp]),
             "sph_slab_plan": (i32, [i32, i32, i32, P(i32), P(i32)]),
             "sph_slab_create": (i32, [P(SphConfig), P(vp)]),
             "sph_slab_info": (i32, [vp, vp]),
@@ -221,6 +223,15 @@ def comm_unique_id():
     """128-byte NCCL id for slab mode (create on rank 0, broadcast to the other ranks)."""
     buf = (C.c_uint8 * 128)()
     rc = cuda_lib().sph_comm_unique_id(buf)
+    if rc:
+        raise SphError(cuda_lib().sph_last_error(None).decode())
+    return bytes(buf)
+
+
+def comm_local_id(world):
+    """128-byte id of the loop-back transport: `world` slab ranks inside this process, one host thread each."""
+    buf = (C.c_uint8 * 128)()
+    rc = cuda_lib().sph_comm_local_id(int(world), buf)
     if rc:
         raise SphError(cuda_lib().sph_last_error(None).decode())
     return bytes(buf)

@@ -5,7 +5,11 @@
 #include "../../include/sph_cuda.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -79,6 +83,31 @@ struct sph_context {
     uint32_t in_off = 0;  // the next grid build reads A[in_off, in_off + n)
 };
 
+// ---- loop-back transport ----------------------------------------------------------------------------
+// The slab exchange needs two operations from its transport: "tell both neighbours how many particles are coming"
+// and "deliver the face buffers into the neighbour's tail".  Between processes that is NCCL send/recv (below).
+// The loop-back transport provides the same two operations between `world` contexts that live in ONE process (on
+// one device or several): every rank runs in its own host thread exactly like a rank process would, counts travel
+// through a mailbox in host memory and payloads as device-to-device copies ordered by CUDA events.  It exists so
+// that the k-slab == 1-GPU equivalence can be checked bit for bit on a one-GPU box; everything above
+// the transport (packing, ghost layers, ownership, overlap schedule) is the code the NCCL runs use.
+struct LocalEdge {  // one direction of one face: src -> dst
+    std::mutex m;
+    std::condition_variable cv;
+    uint64_t posted = 0, consumed = 0;
+    int count = 0;
+    const float4 *pos = nullptr, *vel = nullptr;
+    cudaEvent_t packed = nullptr;  // sender: face buffers complete
+    cudaEvent_t copied = nullptr;  // receiver: face buffers read, may be overwritten
+    bool aborted = false;
+};
+struct LocalComm {
+    int world = 0;
+    std::unique_ptr<LocalEdge[]> up, down;  // up[r]: r -> r + 1, down[r]: r -> r - 1
+    std::atomic<int> refs{0};
+};
+constexpr char kLocalMagic[8] = {'S', 'P', 'H', 'L', 'O', 'O', 'P', '1'};
+
 // One rank of a 1-D slab decomposition along z (the slowest cell axis, so a slab is a contiguous key range
 // and, after the sort, a contiguous particle range).
 struct Slab {
@@ -90,6 +119,7 @@ struct Slab {
     float4 *down_pos = nullptr, *down_vel = nullptr, *up_pos = nullptr, *up_vel = nullptr;
     int *d_counters = nullptr;  // [0] to lower, [1] to upper, [2] from lower, [3] from upper
     ncclComm_t comm = nullptr;
+    LocalComm *local = nullptr;  // loop-back transport instead of NCCL (all ranks in this process)
     uint64_t sent_particles = 0, exchanges = 0;
     // overlapped exchange: pack + NCCL run on their own stream while the interior of the slab is still computing
     cudaStream_t comm_stream = nullptr;
@@ -333,6 +363,25 @@ void slab_release(sph_context *c) {
     if (s->comm) {
         if (NcclApi *api = nccl_api(nullptr)) api->CommDestroy(s->comm);
     }
+    if (s->local) {
+        // wake neighbours that may be blocked on this rank, then drop the shared mailbox with the last rank
+        LocalComm *lc = s->local;
+        for (LocalEdge *e : {s->rank + 1 < s->world ? &lc->up[s->rank] : nullptr, s->rank > 0 ? &lc->down[s->rank] : nullptr,
+                             s->rank > 0 ? &lc->up[s->rank - 1] : nullptr, s->rank + 1 < s->world ? &lc->down[s->rank + 1] : nullptr})
+            if (e) {
+                std::lock_guard<std::mutex> g(e->m);
+                e->aborted = true;
+                e->cv.notify_all();
+            }
+        if (lc->refs.fetch_sub(1) == 1) {
+            for (int r = 0; r < lc->world; ++r)
+                for (LocalEdge *e : {&lc->up[r], &lc->down[r]}) {
+                    if (e->packed) cudaEventDestroy(e->packed);
+                    if (e->copied) cudaEventDestroy(e->copied);
+                }
+            delete lc;
+        }
+    }
     for (void *p : {(void *)s->down_pos, (void *)s->down_vel, (void *)s->up_pos, (void *)s->up_vel, (void *)s->d_counters})
         if (p) cudaFree(p);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
@@ -357,7 +406,19 @@ void slab_plan(int rz, int world, int rank, int *z0, int *z1) {
 // The exchange is split in three stream-ordered pieces so that the overlapped step can run them on the
 // communication stream: pack (one or two index ranges of A), counts (4-byte messages, then read back),
 // payload (exact sizes, received straight into the tail of A).
-void slab_pack_begin(sph_context *c, cudaStream_t st) { cudaMemsetAsync(c->slab->d_counters, 0, 4 * sizeof(int), st); }
+void slab_pack_begin(sph_context *c, cudaStream_t st) {
+    Slab &s = *c->slab;
+    if (s.local) {
+        // the face buffers are about to be overwritten: the neighbours must have copied the previous message out
+        for (LocalEdge *e : {s.rank + 1 < s.world ? &s.local->up[s.rank] : nullptr, s.rank > 0 ? &s.local->down[s.rank] : nullptr}) {
+            if (!e) continue;
+            std::unique_lock<std::mutex> g(e->m);
+            e->cv.wait(g, [&] { return e->consumed == e->posted || e->aborted; });
+            if (e->posted > 0 && !e->aborted) cudaStreamWaitEvent(st, e->copied, 0);
+        }
+    }
+    cudaMemsetAsync(s.d_counters, 0, 4 * sizeof(int), st);
+}
 
 void slab_pack_range(sph_context *c, cudaStream_t st, uint32_t first, uint32_t count) {
     Slab &s = *c->slab;
@@ -368,8 +429,74 @@ void slab_pack_range(sph_context *c, cudaStream_t st, uint32_t first, uint32_t c
 }
 
 // counts[0..1] = particles this rank sends down/up, counts[2..3] = particles it will receive from below/above
+int local_exchange_counts(sph_context *c, cudaStream_t st, int counts[4]) {
+    Slab &s = *c->slab;
+    const bool has_down = s.rank > 0, has_up = s.rank + 1 < s.world;
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_pinned, s.d_counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaEventRecord(s.ev_counts, st));
+    CUDA_TRY(c, cudaEventSynchronize(s.ev_counts));
+    counts[0] = s.h_pinned[0];
+    counts[1] = s.h_pinned[1];
+    REQUIRE(c, counts[0] <= s.cap_face && counts[1] <= s.cap_face, SPH_ERR_STATE, "slab: face buffer overflow");
+    auto post = [&](LocalEdge &e, int count, const float4 *pos, const float4 *vel) -> int {
+        std::lock_guard<std::mutex> g(e.m);
+        e.count = count;
+        e.pos = pos;
+        e.vel = vel;
+        CUDA_TRY(c, cudaEventRecord(e.packed, st));
+        e.posted += 1;
+        e.cv.notify_all();
+        return SPH_OK;
+    };
+    if (has_down)
+        if (int rc = post(s.local->down[s.rank], counts[0], s.down_pos, s.down_vel)) return rc;
+    if (has_up)
+        if (int rc = post(s.local->up[s.rank], counts[1], s.up_pos, s.up_vel)) return rc;
+    auto peek = [&](LocalEdge &e, int *count) -> int {
+        std::unique_lock<std::mutex> g(e.m);
+        e.cv.wait(g, [&] { return e.posted > e.consumed || e.aborted; });
+        REQUIRE(c, !e.aborted, SPH_ERR_COMM, "slab (loop-back): a neighbouring rank was destroyed");
+        *count = e.count;
+        return SPH_OK;
+    };
+    counts[2] = counts[3] = 0;
+    if (has_down)
+        if (int rc = peek(s.local->up[s.rank - 1], &counts[2])) return rc;
+    if (has_up)
+        if (int rc = peek(s.local->down[s.rank + 1], &counts[3])) return rc;
+    return SPH_OK;
+}
+
+int local_exchange_payload(sph_context *c, cudaStream_t st, const int counts[4], uint32_t dst_first) {
+    Slab &s = *c->slab;
+    const bool has_down = s.rank > 0, has_up = s.rank + 1 < s.world;
+    REQUIRE(c, (uint64_t)dst_first + (uint64_t)counts[2] + (uint64_t)counts[3] <= c->cap, SPH_ERR_STATE,
+            "slab: local particle capacity exceeded");
+    float4 *rp = c->pos_a + dst_first, *rv = c->vel_a + dst_first;
+    auto take = [&](LocalEdge &e, float4 *dp, float4 *dv, int count) -> int {
+        std::lock_guard<std::mutex> g(e.m);
+        CUDA_TRY(c, cudaStreamWaitEvent(st, e.packed, 0));
+        if (count) {
+            CUDA_TRY(c, cudaMemcpyAsync(dp, e.pos, (size_t)count * sizeof(float4), cudaMemcpyDefault, st));
+            CUDA_TRY(c, cudaMemcpyAsync(dv, e.vel, (size_t)count * sizeof(float4), cudaMemcpyDefault, st));
+        }
+        CUDA_TRY(c, cudaEventRecord(e.copied, st));
+        e.consumed += 1;
+        e.cv.notify_all();
+        return SPH_OK;
+    };
+    if (has_down)
+        if (int rc = take(s.local->up[s.rank - 1], rp, rv, counts[2])) return rc;
+    if (has_up)
+        if (int rc = take(s.local->down[s.rank + 1], rp + counts[2], rv + counts[2], counts[3])) return rc;
+    s.sent_particles += (uint64_t)counts[0] + (uint64_t)counts[1];
+    s.exchanges += 1;
+    return SPH_OK;
+}
+
 int slab_exchange_counts(sph_context *c, cudaStream_t st, int counts[4]) {
     Slab &s = *c->slab;
+    if (s.local) return local_exchange_counts(c, st, counts);
     NcclApi *api = nccl_api(&c->err);
     if (!api) return SPH_ERR_COMM;
     const bool has_down = s.rank > 0, has_up = s.rank + 1 < s.world;
@@ -396,6 +523,7 @@ int slab_exchange_counts(sph_context *c, cudaStream_t st, int counts[4]) {
 
 int slab_exchange_payload(sph_context *c, cudaStream_t st, const int counts[4], uint32_t dst_first) {
     Slab &s = *c->slab;
+    if (s.local) return local_exchange_payload(c, st, counts, dst_first);
     NcclApi *api = nccl_api(&c->err);
     if (!api) return SPH_ERR_COMM;
     const bool has_down = s.rank > 0, has_up = s.rank + 1 < s.world;
@@ -1013,7 +1141,7 @@ int sph_step(sph_context *c, int n_steps, double *ms) {
     REQUIRE(c, n_steps >= 0, SPH_ERR_ARGUMENT, "sph_step: negative step count");
     CUDA_TRY(c, cudaSetDevice(c->device));
     if (c->slab) return slab_step(c, n_steps, ms);
-    if (n_steps == 0 || c->n == 0) {
+    if (n_steps == 0 || (c->n == 0 && !c->emit_templates)) {
         if (ms) *ms = 0.0;
         return SPH_OK;
     }
@@ -1346,9 +1474,9 @@ int sph_stats(sph_context *c, double *out6) {
     return check_launch(c, "stats");
 }
 
-// Exact order statistic of the fill height y + b/2 by two histogram passes: 4096 bins over the box, then 4096 bins
-// inside the bin that holds rank k = floor(q (n - 1)) (the definition oracle_stats uses).  The answer
-// is the centre of a sub-bin of width box_y / 4096^2 — far below fp32 resolution of the coordinate.
+// Order statistic of the fill height y + b/2 by a min/max pass and two histogram passes: 4096 bins over [ymin, ymax],
+// then 4096 bins inside the bin that holds rank k = floor(q (n - 1)) (the definition oracle_stats uses, SURVEY.md
+// §8c).  The answer is the centre of a sub-bin of width (ymax - ymin) / 4096^2 — below fp32 resolution of y.
 int sph_fill_height_percentile(sph_context *c, double q, double *height) {
     REQUIRE(c, c && height, SPH_ERR_ARGUMENT, "sph_fill_height_percentile: NULL argument");
     REQUIRE(c, q >= 0.0 && q <= 1.0, SPH_ERR_ARGUMENT, "sph_fill_height_percentile: q outside [0, 1]");
@@ -1356,16 +1484,30 @@ int sph_fill_height_percentile(sph_context *c, double q, double *height) {
     CUDA_TRY(c, cudaSetDevice(c->device));
     *height = 0.0;
     if (c->n == 0) return SPH_OK;
+    // range of the finite y values (particles may sit outside the box: the walls are penalty forces)
+    launch_minmax_y(view_pos(c), (int)c->n, c->d_hist, c->stream);
+    c->kernel_launches += 1;
+    unsigned mm[2];
+    CUDA_TRY(c, cudaMemcpyAsync(mm, c->d_hist, sizeof(mm), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    REQUIRE(c, mm[0] <= mm[1], SPH_ERR_STATE, "sph_fill_height_percentile: no particle has a finite y coordinate");
+    auto from_ordered = [](unsigned u) {
+        u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+        float f;
+        std::memcpy(&f, &u, sizeof(f));
+        return (double)f;
+    };
+    const double ymin = from_ordered(mm[0]), ymax = from_ordered(mm[1]);
     const uint64_t k = (uint64_t)(q * (double)(c->n - 1));
     std::vector<unsigned> h(kHistBins);
-    double lo = -(double)c->cfg.box[1] / 2.0, width = (double)c->cfg.box[1] / kHistBins;
+    double lo = ymin, width = std::max((ymax - ymin) * (1.0 + 1e-9), 1e-30) / kHistBins;
     uint64_t below = 0;  // particles in bins before the selected one
     for (int pass = 0; pass < 2; ++pass) {
         launch_hist_y(view_pos(c), (int)c->n, lo, 1.0 / width, pass == 0 ? 1 : 0, c->d_hist, c->stream);
         c->kernel_launches += 1;
         CUDA_TRY(c, cudaMemcpyAsync(h.data(), c->d_hist, kHistBins * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        // pass 0 clamps out-of-box particles into the edge bins; pass 1 only counts particles of the selected bin
+        // pass 0 puts non-finite values into bin 0 (clamped); pass 1 only counts particles of the selected bin
         uint64_t run = pass == 0 ? 0 : below;
         int b = 0;
         for (; b < kHistBins - 1; ++b) {
@@ -1437,6 +1579,18 @@ int sph_comm_unique_id(uint8_t out[128]) {
     return SPH_OK;
 }
 
+int sph_comm_local_id(int32_t world, uint8_t out[128]) {
+    REQUIRE(nullptr, out && world >= 1, SPH_ERR_ARGUMENT, "sph_comm_local_id: bad argument");
+    LocalComm *lc = new LocalComm();
+    lc->world = world;
+    lc->up.reset(new LocalEdge[world]);
+    lc->down.reset(new LocalEdge[world]);
+    std::memset(out, 0, 128);
+    std::memcpy(out, kLocalMagic, sizeof(kLocalMagic));
+    std::memcpy(out + sizeof(kLocalMagic), &lc, sizeof(lc));
+    return SPH_OK;  // the mailbox is freed with the last slab context created from this id
+}
+
 int sph_slab_plan(int32_t rz, int32_t world, int32_t rank, int32_t *z0, int32_t *z1) {
     REQUIRE(nullptr, z0 && z1 && world >= 1 && rank >= 0 && rank < world, SPH_ERR_ARGUMENT, "sph_slab_plan: bad argument");
     REQUIRE(nullptr, rz / world >= 4, SPH_ERR_ARGUMENT, "sph_slab_plan: every slab needs at least 4 z-layers");
@@ -1505,7 +1659,25 @@ int sph_slab_create(const sph_config *cfg, sph_context **out) {
     SLAB_TRY(cudaEventCreateWithFlags(&s->ev_counts, cudaEventDisableTiming));
     SLAB_TRY(cudaEventCreateWithFlags(&s->ev_comm, cudaEventDisableTiming));
 #undef SLAB_TRY
-    if (cfg->world > 1) {
+    if (cfg->world > 1 && std::memcmp(cfg->nccl_id, kLocalMagic, sizeof(kLocalMagic)) == 0) {
+        // loop-back transport: the id carries the address of the mailbox shared by the ranks of this process
+        LocalComm *lc = nullptr;
+        std::memcpy(&lc, cfg->nccl_id + sizeof(kLocalMagic), sizeof(lc));
+        if (!lc || lc->world != cfg->world) {
+            sph_destroy(c);
+            *out = nullptr;
+            return fail(nullptr, SPH_ERR_ARGUMENT, "sph_slab_create: loop-back id does not match world");
+        }
+        s->local = lc;
+        lc->refs.fetch_add(1);
+        // this rank creates the events of the edges it SENDS on (they are recorded on its streams)
+        for (LocalEdge *e : {s->rank + 1 < s->world ? &lc->up[s->rank] : nullptr, s->rank > 0 ? &lc->down[s->rank] : nullptr})
+            if (e) {
+                std::lock_guard<std::mutex> g(e->m);
+                if (!e->packed) cudaEventCreateWithFlags(&e->packed, cudaEventDisableTiming);
+                if (!e->copied) cudaEventCreateWithFlags(&e->copied, cudaEventDisableTiming);
+            }
+    } else if (cfg->world > 1) {
         std::string why;
         NcclApi *api = nccl_api(&why);
         if (!api) {

@@ -102,6 +102,7 @@ void launch_stats(const float4 *pos, const float4 *vel, int n, double *out8, cud
 // histogram of floor((y - lo) * inv_width) over kHistBins bins; `clamp` puts out-of-range values into the edge bins,
 // otherwise they are not counted (refinement pass inside one bin)
 constexpr int kHistBins = 4096;
+void launch_minmax_y(const float4 *pos, int n, unsigned *out2, cudaStream_t st);  // ordered-uint bits of min / max finite y
 void launch_hist_y(const float4 *pos, int n, double lo, double inv_width, int clamp, unsigned *hist, cudaStream_t st);
 
 }  // namespace sph

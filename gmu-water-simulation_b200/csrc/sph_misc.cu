@@ -403,6 +403,36 @@ __global__ void __launch_bounds__(256) k_hist_y(const float4 *__restrict__ pos, 
         if (s_hist[b]) atomicAdd(hist + b, s_hist[b]);
 }
 
+// out[0] = min, out[1] = max of the finite y coordinates, as ordered-uint bits (out[0] starts at 0xffffffff, out[1] at 0)
+__global__ void __launch_bounds__(256) k_minmax_y(const float4 *__restrict__ pos, int n, unsigned *__restrict__ out) {
+    unsigned lo = 0xffffffffu, hi = 0u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float y = __ldg(&pos[i].y);
+        if (isfinite(y)) {
+            const unsigned u = ordered_bits(y);
+            lo = min(lo, u);
+            hi = max(hi, u);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(out, lo);
+        atomicMax(out + 1, hi);
+    }
+}
+void launch_minmax_y(const float4 *pos, int n, unsigned *out2, cudaStream_t st) {
+    cudaMemsetAsync(out2, 0xff, sizeof(unsigned), st);
+    cudaMemsetAsync(out2 + 1, 0, sizeof(unsigned), st);
+    if (n <= 0) return;
+    int blocks = (n + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    k_minmax_y<<<blocks, 256, 0, st>>>(pos, n, out2);
+}
+
 void launch_hist_y(const float4 *pos, int n, double lo, double inv_width, int clamp, unsigned *hist, cudaStream_t st) {
     cudaMemsetAsync(hist, 0, kHistBins * sizeof(unsigned), st);
     if (n <= 0) return;

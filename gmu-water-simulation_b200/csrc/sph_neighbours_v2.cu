@@ -15,10 +15,12 @@
 //                    term for true neighbours only; each neighbour is ONE 256-bit gather
 //                    (LDG.E.ENL2.256, sm_100+).
 //
-// Rows start at an index aligned down to 4 and end aligned up; the <= 3 extra slots on either side
-// are masked out of the word (and their rare density contribution is taken out again), so counts and
-// sets stay exact.  (Per-particle geometric pruning of rows/cells was measured and dropped: under
-// SIMT a warp pays for its longest lane, so it only lowered lane utilisation.)
+// Rows start at an index aligned down to 4 and end aligned up; the bits of the <= 3 foreign slots on either
+// side are dropped from the word, and a word in which a foreign slot was within h is rolled back and re-scanned
+// with those slots masked, so counts, sets and the density sum are exact and independent of the array offset.  (Per-particle geometric pruning of rows/cells was measured and
+// dropped: under SIMT a warp pays for its longest lane, so it only lowered lane utilisation.  Staging the
+// candidate rows in shared memory with bulk async copies was built and measured in round 1 — slower, the rows
+// are served well enough by L1 — and removed; DESIGN.md §3.2 keeps the numbers.)
 #include "sph_kernels.h"
 
 namespace sph {
@@ -75,42 +77,65 @@ __device__ __forceinline__ void ld256(const float4 *p, float4 &a, float4 &b) {
         : "l"(p));
 }
 
-// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) -------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(phase)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-constexpr int kStageCap = 256;  // candidates staged per row slot; longer unions fall back to global loads
-
 // ================================================================= density + pressure + hit bitmask
-// Word format: bit 31 = first candidate of the word (index j0), bit 31-k = candidate j0+k.
+// Word format: bit 31 = first candidate of the word (index j0, a multiple of 4), bit 31-k = candidate j0+k.
 // Stored as uint2 {bits, j0 + 31} so that the force pass gets j = (j0 + 31) - msb_index(bits).
-// STAGED: the <= 9 row unions this CTA's 128 consecutive particles can touch are first copied into shared memory
-// with 1-D bulk async copies (one thread per row slot issues three copies, an mbarrier collects the bytes);
-// the candidate loads of the scan are then LDS.128 instead of LDG.128.
-template <bool STAGED>
+//
+// Every row [a, b) of the particle's x-window is scanned in aligned groups of 4 candidates, 8 groups = one word.
+// The first and the last group of a row may contain FOREIGN slots (the sorted array continues with other bins
+// there).  All lanes of a warp run the same unmasked loop; the foreign bits are dropped when the word is finished.
+// A foreign slot that happens to lie within h (possible next to empty cells, rare) would also have added its
+// poly6 term to the sum: such a word is detected by its dropped bits, the accumulator is rolled back to its value at
+// the start of the word and the word is re-scanned with the foreign slots moved to a far-away sentinel — so the
+// density sum only ever contains the candidates of [a, b), each added exactly once, in ascending order.
+//
+// The sum lives in ONE packed accumulator {even, odd} indexed by the parity of the candidate's position INSIDE ITS
+// ROW (j - a), not by its absolute index: the halves are swapped whenever the parity of the row start changes.
+// Together with the roll-back this makes the density a pure function of the particle state — it does not depend on
+// where the sorted array happens to start, so a slab of a multi-GPU run (whose local array has a different offset)
+// produces the same bits as the single-GPU run (tests/test_slab.py: k slabs == 1 GPU bit for bit).
+constexpr float kFar = 1.0e18f;  // sentinel coordinate: (kFar)^2 is finite in fp32 and t = h2 - r2 hugely negative
+
+struct DensityScan {
+    u64 px2, py2, pz2, h22, nz2;
+    u64 acc;        // packed poly6 sum {even-in-row, odd-in-row}
+    unsigned miss;  // sign bits of t for the current word, first candidate in the highest bit shifted in
+};
+
+// MASKED: slots k of the group outside [lo, hi) are foreign and moved out of reach before the arithmetic
+template <bool MASKED>
+__device__ __forceinline__ void scan_group(DensityScan &d, const float *__restrict__ xs, const float *__restrict__ ys,
+                                           const float *__restrict__ zs, const int j, const int lo, const int hi) {
+    ulonglong2 X = __ldg(reinterpret_cast<const ulonglong2 *>(xs + j));
+    const ulonglong2 Y = __ldg(reinterpret_cast<const ulonglong2 *>(ys + j));
+    const ulonglong2 Z = __ldg(reinterpret_cast<const ulonglong2 *>(zs + j));
+    if (MASKED) {
+        float x0, x1, x2, x3;
+        upk(X.x, x0, x1);
+        upk(X.y, x2, x3);
+        x0 = (0 >= lo && 0 < hi) ? x0 : kFar;
+        x1 = (1 >= lo && 1 < hi) ? x1 : kFar;
+        x2 = (2 >= lo && 2 < hi) ? x2 : kFar;
+        x3 = (3 >= lo && 3 < hi) ? x3 : kFar;
+        X.x = pk(x0, x1);
+        X.y = pk(x2, x3);
+    }
+    const u64 t01 = t_exact2(d.px2, d.py2, d.pz2, X.x, Y.x, Z.x, d.h22, d.nz2);
+    const u64 t23 = t_exact2(d.px2, d.py2, d.pz2, X.y, Y.y, Z.y, d.h22, d.nz2);
+    float t0, t1, t2, t3;
+    upk(t01, t0, t1);
+    upk(t23, t2, t3);
+    // t >= 0  <=>  r2 <= h2, and sign(t) is exact (t is never -0): append the sign bits
+    d.miss = __funnelshift_l(__float_as_uint(t0), d.miss, 1);
+    d.miss = __funnelshift_l(__float_as_uint(t1), d.miss, 1);
+    d.miss = __funnelshift_l(__float_as_uint(t2), d.miss, 1);
+    d.miss = __funnelshift_l(__float_as_uint(t3), d.miss, 1);
+    // poly6: sum += max(t,0)^3, branch-free; candidates in ascending order, even / odd slots
+    const u64 c01 = pk(fmaxf(t0, 0.0f), fmaxf(t1, 0.0f)), c23 = pk(fmaxf(t2, 0.0f), fmaxf(t3, 0.0f));
+    d.acc = fma2(c01, mul2(c01, c01), d.acc);
+    d.acc = fma2(c23, mul2(c23, c23), d.acc);
+}
+
 __global__ void __launch_bounds__(128, 8) k_density_mask(const float *__restrict__ xs, const float *__restrict__ ys,
                                                       const float *__restrict__ zs, const float4 *__restrict__ vel,
                                                       const int *__restrict__ key, const int *__restrict__ cell_start,
@@ -119,102 +144,48 @@ __global__ void __launch_bounds__(128, 8) k_density_mask(const float *__restrict
                                                       int *__restrict__ nb_words, int *__restrict__ ovf, int n,
                                                       const __grid_constant__ Params P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    __shared__ __align__(16) float s_x[STAGED ? 9 : 1][STAGED ? kStageCap + 8 : 4];
-    __shared__ __align__(16) float s_y[STAGED ? 9 : 1][STAGED ? kStageCap + 8 : 4];
-    __shared__ __align__(16) float s_z[STAGED ? 9 : 1][STAGED ? kStageCap + 8 : 4];
-    __shared__ int s_base[9], s_cnt[9];  // first staged index of the slot; staged count (0: fall back to global)
-    __shared__ unsigned long long s_bar;
-    if (STAGED) {
-        if (threadIdx.x == 0) mbar_init(&s_bar, 9);
-        __syncthreads();
-        if (threadIdx.x < 9) {
-            const int slot = threadIdx.x;
-            const int p0 = blockIdx.x * blockDim.x, p1 = min(p0 + (int)blockDim.x, n) - 1;
-            const int rxb = P.rx * P.xb, n_bins = P.n_cells * P.xb;
-            const int off = (slot % 3 - 1) * rxb + (slot / 3 - 1) * rxb * P.ry;
-            // every particle's window reaches at most xb + 1 bins to either side of its own bin
-            const int lo = max(__ldg(key + p0) + off - (P.xb + 1), 0), hi = min(__ldg(key + p1) + off + P.xb + 1, n_bins - 1);
-            int base = 0, cnt = 0;
-            if (lo <= hi) {
-                base = __ldg(cell_start + lo) & ~3;
-                cnt = ((__ldg(cell_start + hi + 1) - base + 3) & ~3) + 4;  // + the <= 3 over-scanned slots
-                if (cnt > kStageCap + 8) cnt = 0;
-            }
-            s_base[slot] = base;
-            s_cnt[slot] = cnt;
-            if (cnt > 0) {
-                mbar_arrive_expect_tx(&s_bar, 3u * 4u * (unsigned)cnt);
-                bulk_g2s(s_x[slot], xs + base, 4u * (unsigned)cnt, &s_bar);
-                bulk_g2s(s_y[slot], ys + base, 4u * (unsigned)cnt, &s_bar);
-                bulk_g2s(s_z[slot], zs + base, 4u * (unsigned)cnt, &s_bar);
-            } else {
-                mbar_arrive_expect_tx(&s_bar, 0u);
-            }
-        }
-        __syncthreads();  // s_base / s_cnt visible
-    }
     if (i >= n) return;
     const float px = __ldg(xs + i), py = __ldg(ys + i), pz = __ldg(zs + i);
-    const u64 px2 = pk(px, px), py2 = pk(py, py), pz2 = pk(pz, pz), h22 = pk(P.h2, P.h2);
-    const u64 nz2 = pk(P.neg_zero, P.neg_zero);
+    DensityScan d;
+    d.px2 = pk(px, px);
+    d.py2 = pk(py, py);
+    d.pz2 = pk(pz, pz);
+    d.h22 = pk(P.h2, P.h2);
+    d.nz2 = pk(P.neg_zero, P.neg_zero);
+    d.acc = 0ull;  // (+0.0f, +0.0f)
+    d.miss = 0u;
     uint2 *const wbase = mask + ((size_t)(i >> 5) * kMaskWords) * 32 + (i & 31);
-    if (STAGED) mbar_wait(&s_bar, 0);
-    u64 sum_a = 0ull, sum_b = 0ull;  // two packed accumulators (+0.0f, +0.0f)
-    float stray_sum = 0.0f;
     int cnt = 0, widx = 0;
-    for_each_window_slot(px, __ldg(key + i), cell_start, P, [&](const int slot, const int a, const int b) {
+    int parity = 0;  // parity of the row start the accumulator halves are currently aligned with
+    for_each_window_slot(px, __ldg(key + i), cell_start, P, [&](const int, const int a, const int b) {
+        if (a >= b) return;
+        if ((a ^ parity) & 1) {  // {even, odd} is relative to the row start: swap the halves when its parity flips
+            float e, o;
+            upk(d.acc, e, o);
+            d.acc = pk(o, e);
+            parity = a;
+        }
         int j = a & ~3;
-        const bool staged = STAGED && s_cnt[slot] > 0;
-        const int sbase = STAGED ? s_base[slot] : 0;
         while (j < b) {
             const int jw = j;
             const int jend = min(jw + 32, b);
-            unsigned miss = 0;  // sign bits of t, first candidate ends up in the highest bit shifted in
+            const u64 acc_at_word_start = d.acc;
+            d.miss = 0u;
 #pragma unroll 2
-            for (; j < jend; j += 4) {
-                ulonglong2 X, Y, Z;
-                if (staged) {
-                    X = *reinterpret_cast<const ulonglong2 *>(&s_x[STAGED ? slot : 0][j - sbase]);
-                    Y = *reinterpret_cast<const ulonglong2 *>(&s_y[STAGED ? slot : 0][j - sbase]);
-                    Z = *reinterpret_cast<const ulonglong2 *>(&s_z[STAGED ? slot : 0][j - sbase]);
-                } else {
-                    X = __ldg(reinterpret_cast<const ulonglong2 *>(xs + j));
-                    Y = __ldg(reinterpret_cast<const ulonglong2 *>(ys + j));
-                    Z = __ldg(reinterpret_cast<const ulonglong2 *>(zs + j));
-                }
-                const u64 t01 = t_exact2(px2, py2, pz2, X.x, Y.x, Z.x, h22, nz2);
-                const u64 t23 = t_exact2(px2, py2, pz2, X.y, Y.y, Z.y, h22, nz2);
-                float t0, t1, t2, t3;
-                upk(t01, t0, t1);
-                upk(t23, t2, t3);
-                // t >= 0  <=>  r2 <= h2, and sign(t) is exact (t is never -0): append the sign bits
-                miss = __funnelshift_l(__float_as_uint(t0), miss, 1);
-                miss = __funnelshift_l(__float_as_uint(t1), miss, 1);
-                miss = __funnelshift_l(__float_as_uint(t2), miss, 1);
-                miss = __funnelshift_l(__float_as_uint(t3), miss, 1);
-                // poly6: sum += max(t,0)^3, branch-free
-                const u64 c01 = pk(fmaxf(t0, 0.0f), fmaxf(t1, 0.0f)), c23 = pk(fmaxf(t2, 0.0f), fmaxf(t3, 0.0f));
-                sum_a = fma2(c01, mul2(c01, c01), sum_a);
-                sum_b = fma2(c23, mul2(c23, c23), sum_b);
-            }
+            for (; j < jend; j += 4) scan_group<false>(d, xs, ys, zs, j, 0, 4);
             // left-justify (a short last word shifted in fewer than 32 bits), turn misses into hits and keep
             // only the candidates inside [a, b)
-            const int scanned = j - jw;                       // multiple of 4, 4..32
-            unsigned m = ~(miss << (32 - scanned));
-            const int lo = max(a - jw, 0), hi = min(b - jw, 32);  // valid candidate offsets [lo, hi)
+            const int scanned = j - jw;  // multiple of 4, 4..32
+            unsigned m = ~(d.miss << (32 - scanned));
+            const int lo = max(a - jw, 0), hi = min(b - jw, 32);  // candidate offsets of this word inside the row
             const unsigned vm = (0xffffffffu >> lo) & ~((hi < 32) ? (0xffffffffu >> hi) : 0u);
-            // The <= 3 slots scanned before a / after b hold whatever particles are adjacent in the sorted
-            // array - usually cells the sphere cannot reach, but next to empty cells they can be true
-            // neighbours that another row already counts.  Their bits are dropped here; their (rare) density
-            // contribution is recomputed exactly and taken out again at the end.
-            unsigned stray = m & ~vm & ~((scanned < 32) ? (0xffffffffu >> scanned) : 0u);
+            const unsigned foreign_hits = m & ~vm & ~((scanned < 32) ? (0xffffffffu >> scanned) : 0u);
             m &= vm;
-            while (stray) {
-                const int js = jw + __clz(stray);
-                stray &= ~(0x80000000u >> __clz(stray));
-                const float ts = P.h2 - r2_exact(px - __ldg(xs + js), py - __ldg(ys + js), pz - __ldg(zs + js));
-                const float cs = fmaxf(ts, 0.0f);
-                stray_sum = fmaf(cs * cs, cs, stray_sum);
+            if (foreign_hits) {
+                // rare: a foreign slot within h has been added to the sum.  Roll the word back and scan it again with
+                // the foreign slots out of reach (same candidates, same order, now only those of [a, b)).
+                d.acc = acc_at_word_start;
+                for (int jj = jw; jj < jw + scanned; jj += 4) scan_group<true>(d, xs, ys, zs, jj, a - jj, b - jj);
             }
             cnt += __popc(m);
             if (m) {  // empty words are not stored at all
@@ -223,10 +194,9 @@ __global__ void __launch_bounds__(128, 8) k_density_mask(const float *__restrict
             }
         }
     });
-    float s0, s1, s2, s3;
-    upk(sum_a, s0, s1);
-    upk(sum_b, s2, s3);
-    float sum = ((s0 + s1) + (s2 + s3)) - stray_sum;
+    float s_even, s_odd;
+    upk(d.acc, s_even, s_odd);
+    float sum = s_even + s_odd;  // commutative: independent of which half is which
     if (!(px < 1.0e17f)) {
         // a particle with a non-finite coordinate (sentinel in xs/ys/zs): in the reference every comparison with NaN
         // is false, so it has no neighbours at all, not even itself -> density 0 (src/CCPUParticleSimulator.cpp:122-127)
@@ -254,12 +224,8 @@ void launch_density_mask(const NbBuffers &nb, const float4 *vel_s, const int *ke
     if (n <= 0) return;
     // k_rank_scatter leaves the list empty; only a second density pass on the same grid needs the explicit reset
     if (reset_overflow_list) cudaMemsetAsync(nb.ovf, 0, sizeof(int), st);
-    if (P.tuning & 2)
-        k_density_mask<true><<<(n + 127) / 128, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, vel_s, key_s, cell_start, dp, nb.fdat,
-                                                              nb.mask, nb_count, nb.words, nb.ovf, n, P);
-    else
-        k_density_mask<false><<<(n + 127) / 128, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, vel_s, key_s, cell_start, dp, nb.fdat,
-                                                               nb.mask, nb_count, nb.words, nb.ovf, n, P);
+    k_density_mask<<<(n + 127) / 128, 128, 0, st>>>(nb.xs, nb.ys, nb.zs, vel_s, key_s, cell_start, dp, nb.fdat, nb.mask,
+                                                    nb_count, nb.words, nb.ovf, n, P);
 }
 
 // ================================================================= forces from the bitmask

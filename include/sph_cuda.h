@@ -196,6 +196,12 @@ int sph_get_counter(const sph_context *ctx, const char *name, uint64_t *value); 
  * nccl_id; max_particles is this rank's capacity (owned + ghost particles).  Every step exchanges, per face, the
  * two boundary layers (ghosts) and the particles that crossed the face (migration) with ncclSend/ncclRecv. ---- */
 int sph_comm_unique_id(uint8_t out[128]);
+/* Loop-back transport: an id for `world` slab contexts that all live in THIS process (one device or several), to be
+ * passed as nccl_id.  Each rank must then be stepped from its own host thread (the exchange blocks until both
+ * neighbours take part, like NCCL ranks do); counts travel through host memory, payloads as device-to-device
+ * copies ordered by CUDA events.  Everything above the transport is shared with the NCCL path — it exists so that
+ * k slabs == 1 GPU can be verified bit for bit on a one-GPU box. */
+int sph_comm_local_id(int32_t world, uint8_t out[128]);
 int sph_slab_plan(int32_t rz, int32_t world, int32_t rank, int32_t *z0, int32_t *z1); /* owned layers [z0, z1) */
 int sph_slab_create(const sph_config *cfg, sph_context **out);
 /* out8 = rank, world, z0, z1, first local layer, local layers, owned particles, mean particles sent per step */

@@ -120,6 +120,108 @@ def test_single_rank_slab_equals_plain_run(gws):
     assert np.array_equal(b["position"].view(np.uint32), c["position"].view(np.uint32))
 
 
+def run_loopback_slabs(gws, box, world, steps, gravity=None, device_of_rank=None, overlap=True):
+    """`world` slab ranks inside this process over the loop-back transport (sph_comm_local_id), each stepped from
+    its own host thread like a rank process would; returns the merged owned particles sorted by id + the contexts' info."""
+    import threading
+
+    ident = gws.comm_local_id(world)
+    sims = []
+    for rank in range(world):
+        dev = device_of_rank(rank) if device_of_rank else 0
+        sim = gws.Simulator("cuda", box, device=dev).enable_slab(rank, world, ident).setup_scene()
+        if gravity is not None:
+            sim.set_gravity(gravity)
+        if not overlap:
+            sim.context().set_option("slab_overlap", 0)
+        sims.append(sim)
+    errors = []
+
+    def work(sim):
+        try:
+            sim.step_many(steps)
+        except Exception as exc:  # noqa: BLE001 - reported by the main thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(sim,)) for sim in sims]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    assert not any(t.is_alive() for t in threads), "a slab rank is stuck in the exchange"
+    assert not errors, errors
+    parts = [sim.context().download_owned() for sim in sims]
+    infos = [sim.context().slab_info() for sim in sims]
+    far = [sim.context().counter("slab_far_movers") for sim in sims]
+    merged = np.concatenate(parts)
+    merged = merged[np.argsort(merged["id"], kind="stable")]
+    for sim in sims:
+        sim.close()
+    return merged, parts, infos, far
+
+
+def assert_same_as_plain(gws, merged, box, steps, gravity=None):
+    plain = gws.Simulator("cuda", box).setup_scene()
+    if gravity is not None:
+        plain.set_gravity(gravity)
+    plain.step_many(steps)
+    plain.sync_host()
+    hp = plain.host_particles()
+    assert merged.shape[0] == plain.n, "the slabs do not hold every particle exactly once"
+    assert np.array_equal(merged["id"], np.arange(plain.n, dtype=np.uint32)), "owned sets are not a partition of the ids"
+    for f in ("cell_id", "grid_position", "position", "velocity", "density", "pressure", "acceleration"):
+        same = merged[f].view(np.uint32) == hp[f].view(np.uint32)
+        assert same.all(), f"{f}: {(~same).sum()} words differ from the single-GPU run"
+    plain.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("overlap", [True, False])
+def test_loopback_slabs_equal_one_gpu_small_tank_with_migration(gws, world, overlap):
+    """k slabs over the loop-back transport == one GPU, BIT FOR BIT, on a small tank whose water is pushed along z
+    (gravity tilted towards +z) so that particles keep migrating across the slab faces for 60 steps."""
+    box, steps, g = (0.5, 0.5, 1.7), 60, (0.0, -9.80665, 6.0)
+    merged, parts, infos, far = run_loopback_slabs(gws, box, world, steps, gravity=g, overlap=overlap)
+    assert far == [0] * world
+    # migration really happened: the ranks no longer own the particles they started with
+    rz = int(gws.make_config(box, 1).grid_res[2])
+    start = gws.Simulator("scene_only", box).setup_scene().host_particles()
+    layer0 = np.clip(np.floor((start["position"][:, 2].astype(np.float64) + np.float32(box[2]) / 2.0) / np.float64(np.float32(0.0457))), 0, rz - 1)
+    moved = 0
+    for rank, part in enumerate(parts):
+        z0, z1 = gws.slab_plan(rz, world, rank)
+        l0 = layer0[part["id"]]
+        moved += int(((l0 < z0) | (l0 >= z1)).sum())
+    assert moved > 50, moved
+    assert_same_as_plain(gws, merged, box, steps, gravity=g)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_loopback_slabs_equal_one_gpu_4m_tank(gws, world):
+    """SURVEY.md §8e equivalence case: the 4,000,000-particle tank 4.56 x 4.56 x 9.13 (100 x 100 x 200 cells), k = 2
+    and 4 slabs vs one GPU after 12 steps, bit for bit (keys, positions, velocities, density, pressure, acceleration)."""
+    box, steps = (4.56, 4.56, 9.13), 12
+    merged, parts, infos, far = run_loopback_slabs(gws, box, world, steps)
+    assert merged.shape[0] == 4_000_000 and far == [0] * world
+    assert [i["z1"] - i["z0"] for i in infos] == [200 // world] * world
+    assert_same_as_plain(gws, merged, box, steps)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nproc", [2, 4, 8])
+def test_nccl_slab_equivalence(gws, nproc):
+    """`nproc` ranks on `nproc` GPUs over NCCL vs one GPU (tools/slab_check.py); skipped where the box has fewer GPUs."""
+    if gws.device_count() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    box = ["--box", "0.5", "0.5", str(0.0457 * 4.2 * nproc + 0.9)]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+           "--master-port", str(29540 + nproc), os.path.join(ROOT, "tools", "slab_check.py"), "--steps", "20", "--bitwise"] + box
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "SLAB CHECK OK" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])
+
+
 @pytest.mark.gpu
 def test_two_rank_slab_equivalence(gws):
     """2 ranks on 2 GPUs vs one GPU (tools/slab_check.py); skipped on single-GPU boxes."""

@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--box", type=float, nargs=3, default=[0.5, 0.5, 1.5])
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--no-overlap", action="store_true", help="sequential exchange-then-step instead of the overlapped step")
+    ap.add_argument("--bitwise", action="store_true", help="require positions, velocities, densities bit-identical to the single-GPU run")
+    ap.add_argument("--gz", type=float, default=0.0, help="gravity z component (pushes water across the slab faces)")
     a = ap.parse_args()
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     def log(msg):
@@ -40,6 +42,8 @@ def main():
 
     sim = gws.Simulator("cuda", tuple(a.box), device=local).enable_slab(rank, world, ident[0]).setup_scene()
     ctx = sim.context()
+    if a.gz:
+        sim.set_gravity((0.0, -9.80665, a.gz))
     if a.no_overlap:
         ctx.set_option("slab_overlap", 0)
     info0 = ctx.slab_info()
@@ -59,6 +63,8 @@ def main():
     ref = None
     if rank == 0:
         ref = gws.Simulator("cuda", tuple(a.box), device=local).setup_scene()
+        if a.gz:
+            ref.set_gravity((0.0, -9.80665, a.gz))
     for k, nsteps in enumerate([1, a.steps - 1]):
         sim.step_many(nsteps)
         log(f"stepped {nsteps}")
@@ -70,6 +76,11 @@ def main():
             n = ref.n
             assert merged.shape[0] == n, f"slab ranks hold {merged.shape[0]} particles, the tank has {n}"
             assert np.array_equal(merged["id"], np.arange(n, dtype=np.uint32)), "owned sets are not a partition of the ids"
+            if a.bitwise:
+                for f in ("cell_id", "position", "velocity", "density", "pressure", "acceleration"):
+                    same = merged[f].view(np.uint32) == hp[f].view(np.uint32)
+                    assert same.all(), f"{f}: {(~same).sum()} words differ from the single-GPU run after step {1 if k == 0 else a.steps}"
+                checks[f"bitwise_after_{1 if k == 0 else a.steps}_steps"] = True
             err = np.abs(merged["position"][:, :3] - hp["position"][:, :3]).max()
             checks[f"max_abs_dx_after_{1 if k == 0 else a.steps}_steps"] = float(err)
             if k == 0:
