@@ -56,6 +56,29 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# which hardware unit bounds each neighbour kernel (ncu) and the metric that shows it
+BINDING_ROOF = {
+    "k_density_mask": {"short": "issue+fp32", "name": "instruction issue / fp32 pipe (9.4 instructions per candidate test)",
+                       "metric": "issue_active_frac"},
+    "k_forces_mask": {"short": "l1", "name": "L1 data pipe: one wavefront per gathered neighbour record", "metric": "l1_data_pipe_frac"},
+}
+
+
+def ncu_facts(gws):
+    """profiles/kernel_traffic.json, written by tools/kernel_traffic.py from an `ncu --set full` capture, is keyed by the
+    sha256 of the kernel library it was captured from; a capture of another build is refused (None)."""
+    import hashlib
+
+    path = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        facts = json.load(f)
+    with open(gws.binding._CUDA_SO, "rb") as f:
+        sha = hashlib.sha256(f.read()).hexdigest()
+    return facts if facts.get("so_sha256") == sha else None
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -250,10 +273,21 @@ def run_ours(args):
     sim.step_many(1, timed=False)
     sim.step_many(max(args.preroll - 1, 1), timed=False)
     ctx.synchronize()
+    if not slab:
+        ctx.state_save(1)  # slot 1: the state after the pre-roll (start of the fixed window run further down)
     flush_l2 = args.flush_l2 and not slab  # a slab's working set (GBs) is far larger than L2 anyway
     args.flush_l2 = flush_l2
     ctx.set_option("flush_l2", 1 if flush_l2 else 0)
-    sim.step_many(max(args.warmup, 3))
+    warmup = max(args.warmup, 3)
+    sim.step_many(warmup)
+
+    def mean_neighbours():
+        return ctx.counter("neighbour_pairs") / max(ctx.n, 1)  # of the last density pass, self included
+
+    nb_start = None
+    if not slab:
+        ctx.state_save(0)  # slot 0: the state at the start of the timed window (replayed for the per-kernel split)
+        nb_start = mean_neighbours()
 
     # ---- timed region: exactly K steps, device time from CUDA events on the launching stream
     launches0 = ctx.counter("kernel_launches")
@@ -264,6 +298,7 @@ def run_ours(args):
         barrier()
         wall = time.perf_counter() - wall0
         launches = ctx.counter("kernel_launches") - launches0
+        nb_end = None if slab else mean_neighbours()
         if wall < 1.5 and not slab:  # keep the GPU under the same load long enough for a few clock samples
             ctx.set_option("flush_l2", 0)
             t_end = time.perf_counter() + 1.5
@@ -275,52 +310,57 @@ def run_ours(args):
     value = total_particles * args.steps / (dev_ms * 1e-3)
     if slab:
         finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, dev_ms, wall, launches, total_particles,
-                    clocks, barrier, max_over_ranks)
+                    clocks, barrier, max_over_ranks, gws)
         return
 
-    # ---- same loop with a warm L2 (no eviction), for information
-    ctx.set_option("flush_l2", 0)
-    sim.step_many(3)
-    warm_ms = max_over_ranks(sim.step_many(args.steps))
+    # ---- per-kernel split ON THE SAME STEPS: the window is replayed from the saved state (same particle order in
+    # memory, deterministic arithmetic => identical steps) with CUDA events between the kernel groups
+    ctx.state_restore(0)
+    prof = ctx.step_profiled(args.steps)
+    phase_ms = {k: prof[k] / args.steps for k in ("grid", "density", "forces")}
+    phase_ms["sum"] = sum(phase_ms.values())
+    phase_ms["step_by_events"] = prof["total"] / args.steps
 
-    # ---- per-kernel split with CUDA events around each phase (C ABI phase calls), L2 evicted per step
-    phase_ms = {"grid": 0.0, "density": 0.0, "forces": 0.0, "integrate": 0.0}
-    reps = min(args.steps, 20)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    for _ in range(reps):
-        flush.zero_()
-        flush.view(torch.int32).sum()  # read-back: leaves clean scratch lines, no write-backs inside the timed phases
-        torch.cuda.synchronize()
-        phase_ms["grid"] += ctx.update_grid()
-        phase_ms["density"] += ctx.density_pressure()
-        phase_ms["forces"] += ctx.forces()
-        ctx.collisions()
-        phase_ms["integrate"] += ctx.integrate()
-    phase_ms = {k: v / reps for k, v in phase_ms.items()}
-    ctx.update_grid(); ctx.density_pressure()
-    nb_counts, _ = ctx.neighbours(lists=False)
-    ctx.forces(); ctx.integrate()
-    mean_nb = float(nb_counts.mean())
+    # ---- the same window with a warm L2 (no eviction), for information
+    ctx.set_option("flush_l2", 0)
+    ctx.state_restore(0)
+    warm_ms = max_over_ranks(sim.step_many(args.steps))
+    ctx.set_option("flush_l2", 1 if args.flush_l2 else 0)
+
+    # ---- fixed window, independent of --steps / --warmup: steps preroll+10 .. preroll+210 of the same run
+    ctx.state_restore(1)
+    sim.step_many(10)
+    fixed_steps = 200
+    fixed_ms = sim.step_many(fixed_steps)
+    nb_fixed_end = mean_neighbours()
+    fixed_window = {"value": n * fixed_steps / (fixed_ms * 1e-3), "unit": UNIT, "ms_per_step": fixed_ms / fixed_steps,
+                    "steps": [args.preroll + 10, args.preroll + 10 + fixed_steps], "mean_neighbours_at_end": nb_fixed_end,
+                    "note": "same run, L2 evicted before every step; the cost of a step grows as the water piles up, so this "
+                            "window does not move with --steps / --warmup"}
+    ctx.state_restore(0)  # everything below (e2e, CPU baseline) starts from the state the timed window started from
 
     peak, peak_src = measured_peaks()
     top = max(("density", "forces"), key=lambda k: phase_ms[k])
     kernel_name = {"density": "k_density_mask", "forces": "k_forces_mask"}[top]
-    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-    tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")
-    if os.path.exists(tpath) and workload == "dam_break_1M":
-        with open(tpath) as f:
-            traffic = json.load(f).get(kernel_name)
+    ncu = ncu_facts(gws)  # dram bytes + pipe utilisations per kernel from the committed ncu capture of THIS build, or None
+    facts = (ncu or {}).get("kernels", {}).get(kernel_name) if workload == "dam_break_1M" else None
     top_bytes = KERNEL_ALG_BYTES[top] * n
     top_gbs = top_bytes / (phase_ms[top] * 1e-3) / 1e9
     step_gbs = value / world * ALG_BYTES_PER_PARTICLE_STEP / 1e9
+    binding = BINDING_ROOF[kernel_name]
     roofline = {
-        "bound": "hbm", "kernel": kernel_name, "achieved": top_gbs, "peak": peak, "unit": "GB/s", "frac": top_gbs / peak,
-        "traffic": traffic, "peak_source": peak_src,
-        "alg_bytes_per_launch": top_bytes,
-        "kernel_ms": phase_ms[top],
+        # the contract's HBM figure: ALGORITHMIC bytes / in-window kernel time against the measured copy bandwidth ...
+        "bound": binding["short"], "kernel": kernel_name, "achieved": top_gbs, "peak": peak, "unit": "GB/s", "frac": top_gbs / peak,
+        "traffic": facts["dram_bytes"] if facts else None, "peak_source": peak_src,
+        "alg_bytes_per_launch": top_bytes, "kernel_ms": phase_ms[top],
+        # ... and the roof that actually binds this kernel (ncu), because HBM does not
+        "binding_roof": {"name": binding["name"], "frac": (facts or {}).get(binding["metric"]), "unit": "fraction of peak (ncu)",
+                         "source": (ncu or {}).get("source") if facts else "no ncu capture of this build committed (profiles/kernel_traffic.json is keyed by the library hash)"},
         "step_level": {"alg_bytes_per_particle_step": ALG_BYTES_PER_PARTICLE_STEP, "achieved": step_gbs, "frac": step_gbs / peak},
-        "note": "neighbour kernels are fp32-issue/L1 bound, not HBM bound (SURVEY.md §8d); see profiles/",
+        "note": "neither neighbour kernel is HBM-bound: achieved/peak/frac above are the HBM roofline the north star asks for, "
+                "binding_roof is the unit ncu shows saturated (DESIGN.md section 3.1)",
     }
+    mean_nb = 0.5 * (nb_start + nb_end)
 
     # ---- end to end through the plugin: upload AoS mirror + step + download, every step
     e2e = None
@@ -385,7 +425,8 @@ def run_ours(args):
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "particles_per_gpu": n, "box": list(box), "grid": grid_res,
-                       "preroll_steps": args.preroll, "mean_neighbours": mean_nb,
+                       "preroll_steps": args.preroll, "timed_window_steps": [args.preroll + warmup, args.preroll + warmup + args.steps],
+                       "mean_neighbours": mean_nb, "mean_neighbours_window": [nb_start, nb_end],
                        "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (slab mode pending)",
                        "l2": "L2 evicted (256 MiB scratch write, then read back so that no dirty scratch lines remain) before every timed step" if args.flush_l2 else "no eviction"},
             "clocks": clocks.summary(),
@@ -394,6 +435,7 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "phase_ms": phase_ms,
+            "fixed_window": fixed_window,
             "value_warm_l2": total_particles * args.steps / (warm_ms * 1e-3),
             "wall_ms_per_step": 1e3 * wall / args.steps,
             "device": device_name,
@@ -404,11 +446,52 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def state_checksum(rec):
+    """Order-independent 64-bit checksum of (id, position bits, velocity bits) over a set of particle records."""
+    import numpy as np
+
+    h = rec["id"].astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    for field, mult in (("position", 0xC2B2AE3D27D4EB4F), ("velocity", 0x165667B19E3779F9)):
+        bits = np.ascontiguousarray(rec[field][:, :3]).view(np.uint32).astype(np.uint64)
+        for axis in range(3):
+            h ^= (bits[:, axis] + np.uint64(axis + 1)) * np.uint64(mult)
+            h = (h << np.uint64(13)) | (h >> np.uint64(51))
+    return int(h.sum(dtype=np.uint64))
+
+
+def slab_equivalence(gws, dist, rank, world, local, steps=10):
+    """SURVEY.md section 8e on the bench box itself: the 4,000,000-particle tank 4.56 x 4.56 x 9.13 stepped by `world`
+    slabs over NCCL and by one GPU; the merged slab state must be bit-identical (checksum over ids, positions,
+    velocities of all particles)."""
+    box = (4.56, 4.56, 9.13)
+    ident = [gws.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ident, src=0)
+    sim = gws.Simulator("cuda", box, device=local).enable_slab(rank, world, ident[0]).setup_scene()
+    sim.step_many(steps)
+    owned = sim.context().download_owned()
+    mine = (int(owned.shape[0]), state_checksum(owned), int(sim.context().counter("slab_far_movers")))
+    sim.close()
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    out = None
+    if rank == 0:
+        plain = gws.Simulator("cuda", box, device=local).setup_scene()
+        plain.step_many(steps)
+        rec = plain.context().download_owned()
+        want = state_checksum(rec)
+        got = sum(p[1] for p in parts) & 0xFFFFFFFFFFFFFFFF
+        out = {"tank": "4.56 x 4.56 x 9.13", "particles": int(rec.shape[0]), "steps": steps, "slabs": world,
+               "particles_in_slabs": sum(p[0] for p in parts), "far_movers": sum(p[2] for p in parts),
+               "checksum_one_gpu": f"{want:016x}", "checksum_slabs": f"{got:016x}", "bitwise_identical": got == want}
+        plain.close()
+    return out
+
+
 def finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, dev_ms, wall, launches, total_particles,
-                clocks, barrier, max_over_ranks):
-    """N > 1: e2e (step + read-back of the owned particles every step), per-rank slab facts, the JSON line."""
+                clocks, barrier, max_over_ranks, gws):
+    """N > 1: e2e (upload + step + read-back of the owned particles every step), per-rank slab facts, the JSON line."""
     peak, peak_src = measured_peaks()
-    sim.set_mirror_mode(1)
+    sim.set_mirror_mode(2)  # RoundTrip: every rank uploads its owned 80-byte records, steps, reads them back
     sim.step(2)
     barrier()
     t0 = time.perf_counter()
@@ -420,6 +503,8 @@ def finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, 
     info["far_movers"] = ctx.counter("slab_far_movers")  # particles the boundary-only exchange would have missed: must be 0
     infos = [None] * world
     dist.all_gather_object(infos, info)
+    sim.close()
+    equivalence = None if args.no_equivalence else slab_equivalence(gws, dist, rank, world, local)
     if rank == 0:
         step_gbs = value / world * ALG_BYTES_PER_PARTICLE_STEP / 1e9
         line = {
@@ -433,20 +518,28 @@ def finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, 
                        "particles_conserved": int(sum(i["n_own"] for i in infos)) == WORKLOADS["tank_64M"][1],
                        "l2": "no eviction: the per-GPU working set (GBs) is far larger than the 126 MB L2"},
             "clocks": clocks.summary(),
-            "e2e": {"value": total_particles * args.e2e_steps / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": 0,
+            "e2e": {"value": total_particles * args.e2e_steps / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(80 * total_particles),
                     "d2h_bytes_per_step": int(80 * total_particles), "steps": args.e2e_steps,
                     "ms_per_step": 1e3 * e2e_sec / args.e2e_steps,
-                    "path": "CCUDAParticleSimulator::step() per rank, MirrorMode::Download (owned particles read back every step)"},
+                    "path": "CCUDAParticleSimulator::step() per rank, MirrorMode::RoundTrip (owned 80-byte records uploaded before and read back after every step)"},
             "gpu_launches": int(launches) * world,
-            "roofline": {"bound": "hbm", "kernel": "whole step (per GPU)", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "issue+fp32 / l1 (per-kernel split at N=1)", "kernel": "whole step (per GPU)", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
                          "frac": step_gbs / peak, "traffic": None, "peak_source": peak_src,
-                         "note": "step-level: 260 algorithmic B per particle-step (SURVEY.md §8d); per-kernel split is reported at N=1"},
+                         "note": "step-level: 260 algorithmic B per particle-step (SURVEY.md \u00a78d); per-kernel split is reported at N=1"},
             "cpu_baseline": None,
+            "slab_equivalence": equivalence,
             "wall_ms_per_step": 1e3 * wall / args.steps,
-            "device": sim.device,
+            "device": infos and sim_device_name(gws, local),
         }
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()
+
+
+def sim_device_name(gws, local):
+    try:
+        return gws.device_name(local)
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def main():
@@ -465,6 +558,7 @@ def main():
     ap.add_argument("--no-scaling-baseline", dest="scaling_baseline", action="store_false",
                     help="skip the single-GPU run of the 64M tank (denominator of the strong-scaling series)")
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")
+    ap.add_argument("--no-equivalence", action="store_true", help="N>1: skip the 4M-tank slabs == one GPU checksum run")
     ap.add_argument("--neighbour-variant", type=int, default=None)
     args = ap.parse_args()
     if args.impl == "reference":

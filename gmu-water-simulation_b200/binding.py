@@ -101,6 +101,8 @@ def cuda_lib():
             "sph_last_error": (C.c_char_p, [vp]),
             "sph_upload_particles": (i32, [vp, vp, u32]),
             "sph_append_particles": (i32, [vp, vp, u32]),
+            "sph_state_save": (i32, [vp, i32]),
+            "sph_state_restore": (i32, [vp, i32]),
             "sph_set_emitter": (i32, [vp, vp, u32, u32, u32]),
             "sph_emit": (i32, [vp, P(u32)]),
             "sph_download_particles": (i32, [vp, vp, u32, P(u32)]),
@@ -116,6 +118,7 @@ def cuda_lib():
             "sph_collisions": (i32, [vp, P(dbl)]),
             "sph_integrate": (i32, [vp, P(dbl)]),
             "sph_step": (i32, [vp, i32, P(dbl)]),
+            "sph_step_profiled": (i32, [vp, i32, vp]),
             "sph_synchronize": (i32, [vp]),
             "sph_download_keys": (i32, [vp, vp]),
             "sph_download_permutation": (i32, [vp, vp]),
@@ -318,6 +321,12 @@ class SphContext:
         rec = np.ascontiguousarray(rec, dtype=PARTICLE_DTYPE)
         self._ck(self.lib.sph_append_particles(self._h, _ptr(rec), rec.shape[0]))
 
+    def state_save(self, slot=0):
+        self._ck(self.lib.sph_state_save(self._h, int(slot)))
+
+    def state_restore(self, slot=0):
+        self._ck(self.lib.sph_state_restore(self._h, int(slot)))
+
     def set_emitter(self, templates, group=7, max_count=None):
         rec = np.ascontiguousarray(templates, dtype=PARTICLE_DTYPE)
         self._ck(self.lib.sph_set_emitter(self._h, _ptr(rec) if rec.shape[0] else None, rec.shape[0], int(group),
@@ -393,6 +402,12 @@ class SphContext:
             return ms.value
         self._ck(self.lib.sph_step(self._h, int(n), None))
         return 0.0
+
+    def step_profiled(self, n=1):
+        """n steps with events between the kernel groups: dict of summed ms (grid, density, forces, total)."""
+        out = np.zeros(4, dtype=np.float64)
+        self._ck(self.lib.sph_step_profiled(self._h, int(n), _ptr(out)))
+        return dict(grid=out[0], density=out[1], forces=out[2], total=out[3])
 
     def synchronize(self):
         self._ck(self.lib.sph_synchronize(self._h))

@@ -137,6 +137,11 @@ void CCUDAParticleSimulator::pushNewParticles() {
 void CCUDAParticleSimulator::step() {
     if (m_slab) {  // slab mode: the exchange is part of the fused device step
         try {
+            // RoundTrip: the host vector (this rank's owned particles, ids in the records) is canonical and goes up
+            // before every step, like on a single device
+            if (m_mirrorMode == RoundTrip)
+                m_cuda->check(sph_upload_particles(m_cuda->ctx(), reinterpret_cast<const sph_particle *>(m_clParticles.data()),
+                                                   (uint32_t)m_clParticles.size()), "step upload");
             m_cuda->check(sph_step(m_cuda->ctx(), 1, nullptr), "step");
             if (m_mirrorMode != Resident) syncHostMirror();
         } catch (CUDAException &exc) {
@@ -169,9 +174,9 @@ void CCUDAParticleSimulator::stepMany(int steps, double *deviceMs) {
     if (!m_cuda) throw CUDAException("stepMany before setupScene");
     // The mirror modes keep their meaning across a batch: in RoundTrip the host vector is canonical, so it goes up
     // first; in every non-resident mode the mirror shows the state after the batch (one read-back, not one per step).
-    if (m_mirrorMode == RoundTrip && !m_slab)
-        m_cuda->check(sph_upload_particles(m_cuda->ctx(), reinterpret_cast<const sph_particle *>(m_clParticles.data()), m_deviceCount),
-                      "stepMany upload");
+    if (m_mirrorMode == RoundTrip)
+        m_cuda->check(sph_upload_particles(m_cuda->ctx(), reinterpret_cast<const sph_particle *>(m_clParticles.data()),
+                                           m_slab ? (uint32_t)m_clParticles.size() : m_deviceCount), "stepMany upload");
     if (m_brute && !m_slab) {  // all-pairs semantics go through the phase path
         for (int k = 0; k < steps; ++k) { CBaseParticleSimulator::step(); addIterations(1); }
         if (deviceMs) { m_cuda->check(sph_synchronize(m_cuda->ctx()), "stepMany"); *deviceMs = 0.0; }
@@ -188,7 +193,7 @@ void CCUDAParticleSimulator::setMirrorMode(MirrorMode m) {
     // RoundTrip makes the host vector canonical (it is uploaded before every step, like the reference's OpenCL
     // path).  Entering it after resident steps with a stale mirror would silently rewind the simulation to whatever
     // the mirror last held, so the mirror is brought up to date first.
-    if (m == RoundTrip && m_mirrorMode != RoundTrip && m_cuda && !m_slab) syncHostMirror();
+    if (m == RoundTrip && m_mirrorMode != RoundTrip && m_cuda) syncHostMirror();
     m_mirrorMode = m;
 }
 

@@ -75,6 +75,9 @@ struct sph_context {
     float4 *d_flush = nullptr;
     size_t flush_count = 0;
     std::vector<cudaEvent_t> step_events;
+    // device-side state snapshots (sph_state_save / sph_state_restore): A arrays in their current order
+    float4 *snap_pos[2] = {nullptr, nullptr}, *snap_vel[2] = {nullptr, nullptr};
+    uint32_t snap_n[2] = {0, 0};
     // device-side fountain emitter (sph_set_emitter): templates of the records one step appends
     float4 *d_emit_pos = nullptr, *d_emit_vel = nullptr;
     uint32_t emit_templates = 0, emit_group = 0, emit_max = 0;
@@ -738,6 +741,10 @@ int sph_destroy(sph_context *c) {
         if (p) cudaFree(p);
     if (c->d_flush) cudaFree(c->d_flush);
     if (c->d_mesh_planes) cudaFree(c->d_mesh_planes);
+    for (int k = 0; k < 2; ++k) {
+        if (c->snap_pos[k]) cudaFree(c->snap_pos[k]);
+        if (c->snap_vel[k]) cudaFree(c->snap_vel[k]);
+    }
     if (c->d_emit_pos) cudaFree(c->d_emit_pos);
     if (c->d_emit_vel) cudaFree(c->d_emit_vel);
     if (c->copy_stream) {
@@ -902,6 +909,37 @@ int sph_append_particles(sph_context *c, const sph_particle *aos, uint32_t n_new
     // A stays authoritative; the snapshot S and everything derived from it no longer covers all particles
     c->s_valid = c->grid_valid = c->a_aligned = c->density_valid = c->forces_valid = false;
     return upload_range(c, aos, first, n_new);
+}
+
+// Snapshot / restore of the authoritative state on the device (two slots): positions, velocities and their current
+// array order, so that a run can be replayed EXACTLY — same particle order in memory, hence the same memory access
+// pattern and timing — e.g. to time the per-kernel split on the very steps whose total was timed before.
+int sph_state_save(sph_context *c, int slot) {
+    REQUIRE(c, c && (slot == 0 || slot == 1), SPH_ERR_ARGUMENT, "sph_state_save: slot must be 0 or 1");
+    REQUIRE(c, !c->slab, SPH_ERR_STATE, "sph_state_save: not available in slab mode");
+    REQUIRE(c, c->a_aligned || !c->s_valid, SPH_ERR_STATE, "sph_state_save: call between steps (after integrate)");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (!c->snap_pos[slot]) {
+        CUDA_TRY(c, dalloc(&c->snap_pos[slot], (size_t)c->cap));
+        CUDA_TRY(c, dalloc(&c->snap_vel[slot], (size_t)c->cap));
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->snap_pos[slot], c->pos_a + c->in_off, (size_t)c->n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->snap_vel[slot], c->vel_a + c->in_off, (size_t)c->n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+    c->snap_n[slot] = c->n;
+    return SPH_OK;
+}
+
+int sph_state_restore(sph_context *c, int slot) {
+    REQUIRE(c, c && (slot == 0 || slot == 1), SPH_ERR_ARGUMENT, "sph_state_restore: slot must be 0 or 1");
+    REQUIRE(c, !c->slab, SPH_ERR_STATE, "sph_state_restore: not available in slab mode");
+    REQUIRE(c, c->snap_pos[slot], SPH_ERR_STATE, "sph_state_restore: nothing saved in this slot");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    c->n = c->snap_n[slot];
+    c->in_off = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(c->pos_a, c->snap_pos[slot], (size_t)c->n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->vel_a, c->snap_vel[slot], (size_t)c->n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+    c->s_valid = c->grid_valid = c->a_aligned = c->density_valid = c->forces_valid = false;
+    return SPH_OK;
 }
 
 int sph_set_emitter(sph_context *c, const sph_particle *templates, uint32_t n_templates, uint32_t group, uint32_t max_count) {
@@ -1247,6 +1285,62 @@ int sph_step(sph_context *c, int n_steps, double *ms) {
     return rc ? rc : t.finish();
 }
 
+// The same steps with CUDA events between the kernel groups (direct launches on the context's stream, L2 evicted
+// before every step when the flush_l2 option is on): phase_ms[0..2] = grid build, density pass, forces + walls +
+// integration summed over the steps, phase_ms[3] = sum of the whole-step spans.  For the bench's per-kernel split:
+// the numbers come from the very steps that are being timed, not from a separate phase-by-phase run.
+int sph_step_profiled(sph_context *c, int n_steps, double *phase_ms) {
+    REQUIRE(c, c && phase_ms, SPH_ERR_ARGUMENT, "sph_step_profiled: NULL argument");
+    REQUIRE(c, n_steps >= 0, SPH_ERR_ARGUMENT, "sph_step_profiled: negative step count");
+    REQUIRE(c, !c->slab && !c->emit_templates, SPH_ERR_STATE, "sph_step_profiled: plain contexts only (no slab mode, no emitter)");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    for (int k = 0; k < 4; ++k) phase_ms[k] = 0.0;
+    if (n_steps == 0 || c->n == 0) return SPH_OK;
+    if (c->opt_flush_l2 && !c->d_flush) {
+        c->flush_count = ((size_t)256 << 20) / sizeof(float4);
+        CUDA_TRY(c, dalloc(&c->d_flush, c->flush_count));
+    }
+    while (c->step_events.size() < (size_t)(4 * n_steps)) {
+        cudaEvent_t e;
+        CUDA_TRY(c, cudaEventCreate(&e));
+        c->step_events.push_back(e);
+    }
+    const bool fused = use_mask_passes(c) && c->opt_fuse_integrate;
+    for (int k = 0; k < n_steps; ++k) {
+        if (c->opt_flush_l2) launch_flush_l2(c->d_flush, c->flush_count, c->stream);
+        CUDA_TRY(c, cudaEventRecord(c->step_events[4 * k + 0], c->stream));
+        enqueue_grid(c);
+        CUDA_TRY(c, cudaEventRecord(c->step_events[4 * k + 1], c->stream));
+        enqueue_density(c);
+        CUDA_TRY(c, cudaEventRecord(c->step_events[4 * k + 2], c->stream));
+        if (fused) {
+            launch_forces_mask(c->nb, c->dp, c->nb_count, c->g.key_s, c->g.cell_start, c->acc, 0, (int)c->n, c->P, c->stream,
+                               c->pos_s, c->pos_a, c->vel_a);
+            c->kernel_launches += 2;
+            c->in_off = 0;
+        } else {
+            enqueue_forces(c);
+            enqueue_integrate(c);
+        }
+        CUDA_TRY(c, cudaEventRecord(c->step_events[4 * k + 3], c->stream));
+    }
+    c->steps += (uint64_t)n_steps;
+    c->last_step_n = c->n;
+    c->s_valid = c->grid_valid = c->density_valid = c->forces_valid = c->a_aligned = true;
+    if (int rc = check_launch(c, "step (profiled)")) return rc;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < n_steps; ++k) {
+        float t = 0.f;
+        for (int ph = 0; ph < 3; ++ph) {
+            cudaEventElapsedTime(&t, c->step_events[4 * k + ph], c->step_events[4 * k + ph + 1]);
+            phase_ms[ph] += (double)t;
+        }
+        cudaEventElapsedTime(&t, c->step_events[4 * k], c->step_events[4 * k + 3]);
+        phase_ms[3] += (double)t;
+    }
+    return SPH_OK;
+}
+
 int sph_synchronize(sph_context *c) {
     REQUIRE(c, c, SPH_ERR_ARGUMENT, "NULL context");
     CUDA_TRY(c, cudaSetDevice(c->device));
@@ -1548,6 +1642,17 @@ int sph_get_counter(const sph_context *c, const char *name, uint64_t *value) {
     if (k == "kernel_launches") *value = c->kernel_launches;
     else if (k == "graph_launches") *value = c->graph_launches;
     else if (k == "steps") *value = c->steps;
+    else if (k == "neighbour_pairs") {  // sum of the per-particle neighbour counts of the last density pass (self included)
+        if (cudaSetDevice(c->device) != cudaSuccess) return SPH_ERR_CUDA;
+        sph_context *m = const_cast<sph_context *>(c);
+        launch_sum_i32(c->nb_count, (int)c->n, reinterpret_cast<unsigned long long *>(c->d_stats), c->stream);
+        m->kernel_launches += 1;
+        unsigned long long v = 0;
+        if (cudaMemcpyAsync(&v, c->d_stats, sizeof(v), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess)
+            return SPH_ERR_CUDA;
+        *value = (uint64_t)v;
+    }
     else if (k == "overflow_particles" || k == "slab_far_movers") {
         // overflow_particles: particles of the last density pass whose hit words did not fit;
         // slab_far_movers: particles the boundary-only exchange would have missed (must stay 0).

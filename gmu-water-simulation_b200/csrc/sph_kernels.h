@@ -99,6 +99,7 @@ void launch_mask_lists(const NbBuffers &nb, const float4 *pos_s, const int *key_
                        const long long *offsets_by_id, int *lists, int *counts_by_id, int n, const Params &P, cudaStream_t st);
 void launch_flush_l2(float4 *buf, size_t count, cudaStream_t st);
 void launch_stats(const float4 *pos, const float4 *vel, int n, double *out8, cudaStream_t st);
+void launch_sum_i32(const int *src, int n, unsigned long long *out, cudaStream_t st);
 // histogram of floor((y - lo) * inv_width) over kHistBins bins; `clamp` puts out-of-range values into the edge bins,
 // otherwise they are not counted (refinement pass inside one bin)
 constexpr int kHistBins = 4096;

@@ -441,6 +441,21 @@ void launch_hist_y(const float4 *pos, int n, double lo, double inv_width, int cl
     k_hist_y<<<blocks, 256, 0, st>>>(pos, n, lo, inv_width, clamp, hist);
 }
 
+__global__ void __launch_bounds__(256) k_sum_i32(const int *__restrict__ src, int n, unsigned long long *__restrict__ out) {
+    unsigned long long s = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (unsigned long long)__ldg(src + i);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+void launch_sum_i32(const int *src, int n, unsigned long long *out, cudaStream_t st) {
+    cudaMemsetAsync(out, 0, sizeof(unsigned long long), st);
+    if (n <= 0) return;
+    int blocks = (n + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    k_sum_i32<<<blocks, 256, 0, st>>>(src, n, out);
+}
+
 void launch_stats(const float4 *pos, const float4 *vel, int n, double *out8, cudaStream_t st) {
     cudaMemsetAsync(out8, 0, 8 * sizeof(double), st);
     if (n <= 0) return;

@@ -112,6 +112,11 @@ const char *sph_last_error(const sph_context *ctx); /* ctx may be NULL: error of
 int sph_upload_particles(sph_context *ctx, const sph_particle *aos, uint32_t n);
 /* Fountain emission (src/CBaseParticleSimulator.cpp:187-210): append n_new particles. */
 int sph_append_particles(sph_context *ctx, const sph_particle *aos, uint32_t n_new);
+/* Device-side snapshot of the state (positions, velocities, their array order) in slot 0 or 1, and its exact
+ * restoration: a replay then runs the same steps with the same memory layout (used by the bench to time the
+ * per-kernel split and a fixed window on identical steps).  Call between steps. */
+int sph_state_save(sph_context *ctx, int slot);
+int sph_state_restore(sph_context *ctx, int slot);
 /* The same emission on the device, so that a filling fountain needs no host transfer per step: templates = the
  * records ONE step appends (position, velocity; n_templates = group * nozzles, the reference has one nozzle of
  * group = 7), max_count = m_maxParticlesCount.  With an emitter set, every step of sph_step() starts with
@@ -158,6 +163,9 @@ int sph_collisions(sph_context *ctx, double *ms);        /* no-op: walls are fus
 int sph_integrate(sph_context *ctx, double *ms);         /* wall penalty force + integration fused; ≙ src/CGPUBaseParticleSimulator.cpp:59-97 */
 /* n_steps full steps back to back on the device (CUDA graph), no host transfer; *ms = total device time. */
 int sph_step(sph_context *ctx, int n_steps, double *ms);
+/* The same n_steps with CUDA events between the kernel groups: phase_ms[0..2] = grid build, density pass, forces +
+ * walls + integration (sums over the steps), phase_ms[3] = sum of the whole-step spans.  Direct launches, no graph. */
+int sph_step_profiled(sph_context *ctx, int n_steps, double *phase_ms4);
 int sph_synchronize(sph_context *ctx);
 
 /* ---- validation taps (all arrays indexed by particle id unless stated) ---- */
@@ -188,7 +196,9 @@ int sph_fill_height_percentile(sph_context *ctx, double q, double *height);
 
 /* ---- tuning / introspection ---- */
 int sph_set_option(sph_context *ctx, const char *name, int value);
-int sph_get_counter(const sph_context *ctx, const char *name, uint64_t *value); /* "kernel_launches", "graph_launches", "steps" */
+/* "kernel_launches", "graph_launches", "steps", "overflow_particles", "slab_far_movers", "neighbour_pairs" (sum of the
+ * neighbour counts of the last density pass, self included) */
+int sph_get_counter(const sph_context *ctx, const char *name, uint64_t *value);
 
 /* ---- slab mode (multi-GPU extension; the reference is single-device): 1-D decomposition along z, the slowest
  * cell axis of CGrid::at (include/CGrid.h:27).  One process per GPU; rank 0 creates the NCCL id and the launcher
