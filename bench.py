@@ -217,6 +217,20 @@ def cpu_baseline_sample(pos, vel, box, seconds=12.0):
     return out
 
 
+class JsonOut:
+    """stdout carries exactly one JSON line: file descriptor 1 is pointed at stderr for the whole run (NCCL, the CUDA
+    runtime or a child process may print there), and only emit() writes to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self._out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        self._out.write(json.dumps(line) + "\n")
+        self._out.flush()
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -227,11 +241,13 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    out = JsonOut()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this benchmark has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line, whatever NCCL_DEBUG says
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -310,7 +326,7 @@ def run_ours(args):
     value = total_particles * args.steps / (dev_ms * 1e-3)
     if slab:
         finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, dev_ms, wall, launches, total_particles,
-                    clocks, barrier, max_over_ranks, gws)
+                    clocks, barrier, max_over_ranks, gws, out)
         return
 
     # ---- per-kernel split ON THE SAME STEPS: the window is replayed from the saved state (same particle order in
@@ -441,7 +457,7 @@ def run_ours(args):
             "device": device_name,
             "scaling_baseline": scaling_baseline,
         }
-        print(json.dumps(line), flush=True)
+        out.emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -488,7 +504,7 @@ def slab_equivalence(gws, dist, rank, world, local, steps=10):
 
 
 def finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, dev_ms, wall, launches, total_particles,
-                clocks, barrier, max_over_ranks, gws):
+                clocks, barrier, max_over_ranks, gws, out):
     """N > 1: e2e (upload + step + read-back of the owned particles every step), per-rank slab facts, the JSON line."""
     peak, peak_src = measured_peaks()
     sim.set_mirror_mode(2)  # RoundTrip: every rank uploads its owned 80-byte records, steps, reads them back
@@ -501,6 +517,7 @@ def finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, 
     sim.set_mirror_mode(0)
     info = ctx.slab_info()
     info["far_movers"] = ctx.counter("slab_far_movers")  # particles the boundary-only exchange would have missed: must be 0
+    info["clocks"] = clocks.summary()  # every rank samples its own GPU: the step runs at the pace of the slowest slab
     infos = [None] * world
     dist.all_gather_object(infos, info)
     sim.close()
@@ -518,6 +535,7 @@ def finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, 
                        "particles_conserved": int(sum(i["n_own"] for i in infos)) == WORKLOADS["tank_64M"][1],
                        "l2": "no eviction: the per-GPU working set (GBs) is far larger than the 126 MB L2"},
             "clocks": clocks.summary(),
+            "clocks_per_rank": [i["clocks"] for i in infos],
             "e2e": {"value": total_particles * args.e2e_steps / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(80 * total_particles),
                     "d2h_bytes_per_step": int(80 * total_particles), "steps": args.e2e_steps,
                     "ms_per_step": 1e3 * e2e_sec / args.e2e_steps,
@@ -531,7 +549,7 @@ def finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, 
             "wall_ms_per_step": 1e3 * wall / args.steps,
             "device": infos and sim_device_name(gws, local),
         }
-        print(json.dumps(line), flush=True)
+        out.emit(line)
     dist.destroy_process_group()
 
 

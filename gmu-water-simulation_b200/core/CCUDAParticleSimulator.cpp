@@ -63,8 +63,10 @@ void CCUDAParticleSimulator::setupScene() {
     }
     m_cuda.reset(new CUDAWrapper(cfg, m_slab));
 
-    // page-lock the host mirror once: it never reallocates (reserved to the maximum count in setupScene)
-    if (!m_slab && m_clParticles.capacity() > 0)
+    // page-lock the host mirror once: it never reallocates (reserved to the maximum count in setupScene; in slab mode
+    // to the rank's device capacity, because the owned count drifts as particles migrate)
+    if (m_slab) m_clParticles.reserve(capacity);
+    if (m_clParticles.capacity() > 0)
         sph_pin_host_buffer(m_cuda->ctx(), m_clParticles.data(), m_clParticles.capacity() * sizeof(CParticle::Physics));
 
     pushCollisionFaces();
