@@ -53,7 +53,9 @@ int main(int argc, char **argv) {
         std::fprintf(stderr, "device: %s\nparticles: %lu (max %lu)\n", sim->getSelectedDevice().c_str(), sim->getParticlesCount(),
                      sim->getMaxParticlesCount());
 
-        const bool phase_path = phases || sc == FOUNTAIN || brute || mirror != 0;
+        // the fountain emits on the device (sph_set_emitter) and runs the fused step like the dam break; only --phases,
+        // the all-pairs variant and the mirror modes go through the five separate phase calls
+        const bool phase_path = phases || brute || mirror != 0;
         auto run = [&](int k) {
             if (phase_path) for (int s = 0; s < k; ++s) sim->doWork();
             else sim->stepMany(k);
@@ -67,6 +69,8 @@ int main(int argc, char **argv) {
         double particle_steps = 0;
         if (phase_path) {
             for (int s = 0; s < steps; ++s) { sim->doWork(); particle_steps += (double)sim->getParticlesCount(); }
+        } else if (sc == FOUNTAIN) {  // the particle count grows while the scene fills
+            for (int s = 0; s < steps; ++s) { sim->stepMany(1); particle_steps += (double)sim->getParticlesCount(); }
         } else {
             sim->stepMany(steps);
             particle_steps = (double)steps * (double)sim->getParticlesCount();
