@@ -66,17 +66,13 @@ BINDING_ROOF = {
 
 def ncu_facts(gws):
     """profiles/kernel_traffic.json, written by tools/kernel_traffic.py from an `ncu --set full` capture, is keyed by the
-    sha256 of the kernel library it was captured from; a capture of another build is refused (None)."""
-    import hashlib
-
+    hash of the kernel sources it was captured from; a capture of another build is refused (None)."""
     path = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:
         facts = json.load(f)
-    with open(gws.binding._CUDA_SO, "rb") as f:
-        sha = hashlib.sha256(f.read()).hexdigest()
-    return facts if facts.get("so_sha256") == sha else None
+    return facts if facts.get("kernel_source_sha256") == gws.kernel_source_hash() else None
 
 
 class ClockSampler:
@@ -371,7 +367,7 @@ def run_ours(args):
         "alg_bytes_per_launch": top_bytes, "kernel_ms": phase_ms[top],
         # ... and the roof that actually binds this kernel (ncu), because HBM does not
         "binding_roof": {"name": binding["name"], "frac": (facts or {}).get(binding["metric"]), "unit": "fraction of peak (ncu)",
-                         "source": (ncu or {}).get("source") if facts else "no ncu capture of this build committed (profiles/kernel_traffic.json is keyed by the library hash)"},
+                         "source": (ncu or {}).get("source") if facts else "no ncu capture of this build committed (profiles/kernel_traffic.json is keyed by the hash of the kernel sources)"},
         "step_level": {"alg_bytes_per_particle_step": ALG_BYTES_PER_PARTICLE_STEP, "achieved": step_gbs, "frac": step_gbs / peak},
         "note": "neither neighbour kernel is HBM-bound: achieved/peak/frac above are the HBM roofline the north star asks for, "
                 "binding_roof is the unit ncu shows saturated (DESIGN.md section 3.1)",

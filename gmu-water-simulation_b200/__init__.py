@@ -25,6 +25,7 @@ from .binding import (  # noqa: F401
     device_count,
     device_name,
     host_lib,
+    kernel_source_hash,
     make_config,
     particles_from_arrays,
 )

@@ -71,6 +71,21 @@ def build(verbose=False):
     return _CUDA_SO, _HOST_SO
 
 
+def kernel_source_hash():
+    """sha256 over the kernel library's sources (csrc/*.cu, *.cuh, *.h, Makefile, include/sph_cuda.h): identifies the
+    build an ncu capture belongs to.  (The .so itself is not byte-reproducible across nvcc runs.)"""
+    import hashlib
+
+    h = hashlib.sha256()
+    csrc = os.path.join(_PKG, "csrc")
+    files = sorted(f for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".h")) or f == "Makefile")
+    for path in [os.path.join(csrc, f) for f in files] + [os.path.join(_ROOT, "include", "sph_cuda.h")]:
+        h.update(os.path.basename(path).encode() + b"\0")
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def declared_symbols(header):
     """Function names declared in include/<header> (used by the export test)."""
     text = open(os.path.join(_ROOT, "include", header)).read()

@@ -45,3 +45,29 @@ def test_gpu_arm_refuses_to_run_without_a_device():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "1"], capture_output=True,
                          text=True, timeout=120)
     assert out.returncode != 0 and "no CUDA device" in (out.stderr + out.stdout)
+
+
+def test_ncu_facts_belong_to_the_kernels_in_the_tree(gws):
+    """profiles/kernel_traffic.json (dram bytes and pipe utilisations bench.py reports as roofline.traffic /
+    binding_roof) must come from an ncu capture of the kernel sources that are in the tree; bench.py refuses the file
+    otherwise.  Re-run tools/make_profiles.sh + tools/kernel_traffic.py after changing a kernel."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    facts = bench.ncu_facts(gws)
+    assert facts is not None, "profiles/kernel_traffic.json is stale: it was captured from other kernel sources"
+    for kernel in ("k_density_mask", "k_forces_mask"):
+        k = facts["kernels"][kernel]
+        assert k["dram_bytes"] > 1e7 and 0 < k["issue_active_frac"] < 1 and 0 < k["l1_data_pipe_frac"] < 1
+    path = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    stale = dict(facts, kernel_source_sha256="0" * 64)
+    backup = open(path).read()
+    try:
+        with open(path, "w") as f:
+            json.dump(stale, f)
+        assert bench.ncu_facts(gws) is None
+    finally:
+        with open(path, "w") as f:
+            f.write(backup)

@@ -3,8 +3,9 @@
     ncu -i gpurun_out/<tag>_neighbour_kernels.ncu-rep --page raw --csv > /tmp/raw.csv
     python tools/kernel_traffic.py /tmp/raw.csv "profiles/<tag>_ncu_neighbour_kernels.txt" > profiles/kernel_traffic.json
 
-The file is keyed by the sha256 of gmu-water-simulation_b200/libsph_cuda.so: bench.py only reports `roofline.traffic`
-and `roofline.binding_roof.frac` from it when the library it is timing is the one that was profiled.
+The file is keyed by the sha256 of the kernel sources (gws.kernel_source_hash(); the .so is not byte-reproducible across
+nvcc runs): bench.py only reports `roofline.traffic` and `roofline.binding_roof.frac` from it when the kernels it is
+timing are the ones that were profiled.
 """
 import csv
 import hashlib
@@ -33,8 +34,10 @@ def main():
     rows = list(csv.reader(open(sys.argv[1])))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ix = {h: i for i, h in enumerate(hdr)}
-    so = os.path.join(ROOT, "gmu-water-simulation_b200", "libsph_cuda.so")
-    out = {"so_sha256": hashlib.sha256(open(so, "rb").read()).hexdigest(), "source": sys.argv[2] if len(sys.argv) > 2 else sys.argv[1],
+    sys.path.insert(0, ROOT)
+    import gmu_water_simulation_b200 as gws
+
+    out = {"kernel_source_sha256": gws.kernel_source_hash(), "source": sys.argv[2] if len(sys.argv) > 2 else sys.argv[1],
            "state": "dam break, 1,011,240 particles, step 201 (tools/profile_step.py), one launch each, cold caches under ncu",
            "kernels": {}}
     for r in data:
