@@ -523,6 +523,16 @@ class _BorrowedContext(SphContext):
     __del__ = close
 
 
+class _OwnedArray(np.ndarray):
+    """ndarray view of memory owned by another Python object (kept alive through `_owner`)."""
+
+    _owner = None
+
+    def __array_finalize__(self, obj):
+        if obj is not None and self._owner is None:
+            self._owner = getattr(obj, "_owner", None)
+
+
 class Simulator:
     """The C++ simulator object (CCUDAParticleSimulator / scene-only) through the facade."""
 
@@ -640,7 +650,9 @@ class Simulator:
             return np.zeros(0, dtype=PARTICLE_DTYPE)
         addr = self.lib.gmu_sim_host_particles(self._h)
         buf = (C.c_uint8 * (n * 80)).from_address(addr)
-        return np.frombuffer(buf, dtype=PARTICLE_DTYPE, count=n)
+        view = np.frombuffer(buf, dtype=PARTICLE_DTYPE, count=n).view(_OwnedArray)
+        view._owner = self  # the memory belongs to the C++ simulator: keep it alive as long as any view of it is
+        return view
 
     def context(self):
         h = self.lib.gmu_sim_context(self._h)

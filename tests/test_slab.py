@@ -160,6 +160,21 @@ def run_loopback_slabs(gws, box, world, steps, gravity=None, device_of_rank=None
     return merged, parts, infos, far
 
 
+def migrated_particles(gws, box, world, parts):
+    """How many particles are now owned by another rank than the one whose layers they started in."""
+    rz = int(gws.make_config(box, 1).grid_res[2])
+    scene = gws.Simulator("scene_only", box).setup_scene()  # keep the owner of the host mirror alive while it is read
+    z = scene.host_particles()["position"][:, 2].astype(np.float64)
+    layer0 = np.clip(np.floor((z + np.float32(box[2]) / 2.0) / np.float64(np.float32(0.0457))), 0, rz - 1)
+    scene.close()
+    moved = 0
+    for rank, part in enumerate(parts):
+        z0, z1 = gws.slab_plan(rz, world, rank)
+        l0 = layer0[part["id"]]
+        moved += int(((l0 < z0) | (l0 >= z1)).sum())
+    return moved
+
+
 def assert_same_as_plain(gws, merged, box, steps, gravity=None):
     plain = gws.Simulator("cuda", box).setup_scene()
     if gravity is not None:
@@ -184,16 +199,7 @@ def test_loopback_slabs_equal_one_gpu_small_tank_with_migration(gws, world, over
     box, steps, g = (0.5, 0.5, 1.7), 60, (0.0, -9.80665, 6.0)
     merged, parts, infos, far = run_loopback_slabs(gws, box, world, steps, gravity=g, overlap=overlap)
     assert far == [0] * world
-    # migration really happened: the ranks no longer own the particles they started with
-    rz = int(gws.make_config(box, 1).grid_res[2])
-    start = gws.Simulator("scene_only", box).setup_scene().host_particles()
-    layer0 = np.clip(np.floor((start["position"][:, 2].astype(np.float64) + np.float32(box[2]) / 2.0) / np.float64(np.float32(0.0457))), 0, rz - 1)
-    moved = 0
-    for rank, part in enumerate(parts):
-        z0, z1 = gws.slab_plan(rz, world, rank)
-        l0 = layer0[part["id"]]
-        moved += int(((l0 < z0) | (l0 >= z1)).sum())
-    assert moved > 50, moved
+    assert migrated_particles(gws, box, world, parts) > 50  # the ranks no longer own the particles they started with
     assert_same_as_plain(gws, merged, box, steps, gravity=g)
 
 
@@ -201,12 +207,14 @@ def test_loopback_slabs_equal_one_gpu_small_tank_with_migration(gws, world, over
 @pytest.mark.parametrize("world", [2, 4])
 def test_loopback_slabs_equal_one_gpu_4m_tank(gws, world):
     """SURVEY.md §8e equivalence case: the 4,000,000-particle tank 4.56 x 4.56 x 9.13 (100 x 100 x 200 cells), k = 2
-    and 4 slabs vs one GPU after 12 steps, bit for bit (keys, positions, velocities, density, pressure, acceleration)."""
-    box, steps = (4.56, 4.56, 9.13), 12
-    merged, parts, infos, far = run_loopback_slabs(gws, box, world, steps)
+    and 4 slabs vs one GPU after 14 steps, bit for bit (keys, positions, velocities, density, pressure, acceleration).
+    Gravity is tilted towards +z so that particles cross the slab faces (migration) during the run."""
+    box, steps, g = (4.56, 4.56, 9.13), 14, (0.0, -9.80665, 6.0)
+    merged, parts, infos, far = run_loopback_slabs(gws, box, world, steps, gravity=g)
     assert merged.shape[0] == 4_000_000 and far == [0] * world
     assert [i["z1"] - i["z0"] for i in infos] == [200 // world] * world
-    assert_same_as_plain(gws, merged, box, steps)
+    assert migrated_particles(gws, box, world, parts) > 1000
+    assert_same_as_plain(gws, merged, box, steps, gravity=g)
 
 
 @pytest.mark.gpu
