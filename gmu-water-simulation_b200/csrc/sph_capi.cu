@@ -250,7 +250,7 @@ void enqueue_density(sph_context *c) {
                             !c->ovf_clean),
             c->ovf_clean = false;
     else
-        launch_density(c->pos_s, c->g.key_s, c->g.cell_start, c->dp, c->nb_count, (int)c->n, c->P, 0, c->stream);
+        launch_density(c->pos_s, c->g.key_s, c->g.cell_start, c->dp, c->nb_count, (int)c->n, c->P, c->stream);
     c->kernel_launches += 1;
 }
 void enqueue_forces(sph_context *c) {
@@ -258,7 +258,7 @@ void enqueue_forces(sph_context *c) {
         launch_forces_mask(c->nb, c->dp, c->nb_count, c->g.key_s, c->g.cell_start, c->acc, 0, (int)c->n, c->P, c->stream),
             c->kernel_launches += 1;  // main kernel + the (normally idle) overflow kernel
     else
-        launch_forces(c->pos_s, c->vel_s, c->dp, c->g.key_s, c->g.cell_start, c->acc, (int)c->n, c->P, 0, c->stream);
+        launch_forces(c->pos_s, c->vel_s, c->dp, c->g.key_s, c->g.cell_start, c->acc, (int)c->n, c->P, c->stream);
     c->kernel_launches += 1;
 }
 void enqueue_integrate(sph_context *c) {

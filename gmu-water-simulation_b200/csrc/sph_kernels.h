@@ -42,9 +42,9 @@ void launch_rank_scatter(const float4 *pos_a, const float4 *vel_a, float4 *pos_s
 
 // neighbour passes on the canonical order
 void launch_density(const float4 *pos_s, const int *key_s, const int *cell_start, float4 *dp, int *nb_count, int n,
-                    const Params &P, int variant, cudaStream_t st);
+                    const Params &P, cudaStream_t st);
 void launch_forces(const float4 *pos_s, const float4 *vel_s, const float4 *dp, const int *key_s, const int *cell_start,
-                   float4 *acc, int n, const Params &P, int variant, cudaStream_t st);
+                   float4 *acc, int n, const Params &P, cudaStream_t st);
 void launch_density_mask(const NbBuffers &nb, const float4 *vel_s, const int *key_s, const int *cell_start, float4 *dp,
                          int *nb_count, int n, const Params &P, cudaStream_t st, bool reset_overflow_list);
 // [i0, i1) = index range of the canonical order to process (the whole array outside slab mode)

@@ -47,9 +47,8 @@ __global__ void __launch_bounds__(128) k_density(const float4 *__restrict__ pos,
 }
 
 void launch_density(const float4 *pos_s, const int *key_s, const int *cell_start, float4 *dp, int *nb_count, int n,
-                    const Params &P, int variant, cudaStream_t st) {
+                    const Params &P, cudaStream_t st) {
     if (n <= 0) return;
-    (void)variant;
     k_density<<<(n + 127) / 128, 128, 0, st>>>(pos_s, key_s, cell_start, dp, nb_count, n, P);
 }
 
@@ -130,9 +129,8 @@ __global__ void __launch_bounds__(BLOCK) k_forces(const float4 *__restrict__ pos
 }
 
 void launch_forces(const float4 *pos_s, const float4 *vel_s, const float4 *dp, const int *key_s, const int *cell_start,
-                   float4 *acc, int n, const Params &P, int variant, cudaStream_t st) {
+                   float4 *acc, int n, const Params &P, cudaStream_t st) {
     if (n <= 0) return;
-    (void)variant;
     k_forces<128, 48><<<(n + 127) / 128, 128, 0, st>>>(pos_s, vel_s, dp, key_s, cell_start, acc, n, P);
 }
 
