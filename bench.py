@@ -272,6 +272,7 @@ def run_ours(args):
         ident = [gws.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ident, src=0)
         sim = gws.Simulator("cuda", box, device=local).enable_slab(rank, world, ident[0]).setup_scene()
+        sim.context().set_option("slab_rebalance", args.slab_rebalance)
     else:
         workload = args.workload
         box, _ = WORKLOADS[workload]
@@ -512,6 +513,8 @@ def finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, 
     e2e_sec = max_over_ranks(time.perf_counter() - t0)
     sim.set_mirror_mode(0)
     info = ctx.slab_info()
+    info["face_moves"] = ctx.counter("slab_face_moves")
+    info["load_us"] = ctx.counter("slab_load_us")
     info["far_movers"] = ctx.counter("slab_far_movers")  # particles the boundary-only exchange would have missed: must be 0
     info["clocks"] = clocks.summary()  # every rank samples its own GPU: the step runs at the pace of the slowest slab
     infos = [None] * world
@@ -526,8 +529,9 @@ def finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, 
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "particles": int(total_particles), "box": list(box),
                        "preroll_steps": args.preroll,
-                       "parallelism": f"{world} z-slabs, ghost+migration exchange per step via ncclSend/ncclRecv",
-                       "slabs": [{k: i[k] for k in ("z0", "z1", "n_own", "mean_sent_per_step", "far_movers")} for i in infos],
+                       "parallelism": f"{world} z-slabs, ghost+migration exchange per step via ncclSend/ncclRecv; "
+                                      + ("faces follow the measured load" if args.slab_rebalance else "static equal-layer faces"),
+                       "slabs": [{k: i[k] for k in ("z0", "z1", "n_own", "mean_sent_per_step", "far_movers", "face_moves", "load_us")} for i in infos],
                        "particles_conserved": int(sum(i["n_own"] for i in infos)) == WORKLOADS["tank_64M"][1],
                        "l2": "no eviction: the per-GPU working set (GBs) is far larger than the 126 MB L2"},
             "clocks": clocks.summary(),
@@ -572,6 +576,8 @@ def main():
     ap.add_argument("--no-scaling-baseline", dest="scaling_baseline", action="store_false",
                     help="skip the single-GPU run of the 64M tank (denominator of the strong-scaling series)")
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false")
+    ap.add_argument("--slab-rebalance", type=int, default=1, choices=[0, 1],
+                    help="N>1: 1 = the faces between slabs follow the measured load (default), 0 = static equal-layer split")
     ap.add_argument("--no-equivalence", action="store_true", help="N>1: skip the 4M-tank slabs == one GPU checksum run")
     ap.add_argument("--neighbour-variant", type=int, default=None)
     args = ap.parse_args()

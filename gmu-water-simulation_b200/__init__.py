@@ -19,6 +19,7 @@ from .binding import (  # noqa: F401
     comm_local_id,
     comm_unique_id,
     simulation_type,
+    slab_face_shift,
     slab_plan,
     cuda_lib,
     declared_symbols,

@@ -152,6 +152,7 @@ def cuda_lib():
             "sph_comm_local_id": (i32, [i32, vp]),
             "sph_slab_plan": (i32, [i32, i32, i32, P(i32), P(i32)]),
             "sph_slab_create": (i32, [P(SphConfig), P(vp)]),
+            "sph_slab_face_shift": (i32, [vp, vp, i32, i32, i32, u64, i32]),
             "sph_slab_info": (i32, [vp, vp]),
             "sph_download_owned": (i32, [vp, vp, u32, P(u32)]),
         }
@@ -253,6 +254,13 @@ def comm_local_id(world):
     if rc:
         raise SphError(cuda_lib().sph_last_error(None).decode())
     return bytes(buf)
+
+
+def slab_face_shift(lower, upper, shift=0, shift_max=8, mode=1, exchange=0, face=0):
+    """The rule both ranks at a slab face apply to the records {load_us, z0, z1, may_grow} of the lower / upper rank."""
+    lo = np.asarray(lower, dtype=np.int32)
+    hi = np.asarray(upper, dtype=np.int32)
+    return int(cuda_lib().sph_slab_face_shift(_ptr(lo), _ptr(hi), int(shift), int(shift_max), int(mode), int(exchange), int(face)))
 
 
 def slab_plan(rz, world, rank):

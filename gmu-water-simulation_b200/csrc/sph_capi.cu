@@ -99,6 +99,7 @@ struct LocalEdge {  // one direction of one face: src -> dst
     std::condition_variable cv;
     uint64_t posted = 0, consumed = 0;
     int count = 0;
+    int aux[4] = {0, 0, 0, 0};     // the sender's {load, z0, z1, can_grow} (face rebalancing, see Slab)
     const float4 *pos = nullptr, *vel = nullptr;
     cudaEvent_t packed = nullptr;  // sender: face buffers complete
     cudaEvent_t copied = nullptr;  // receiver: face buffers read, may be overwritten
@@ -128,9 +129,44 @@ struct Slab {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_ranges = nullptr, ev_boundary = nullptr, ev_counts = nullptr, ev_comm = nullptr;
     bool have_ghosts = false;  // A already holds this step's ghosts/migrants behind the owned particles
-    int *h_pinned = nullptr;   // 8 ints of pinned host memory for the small read-backs
+    int *h_pinned = nullptr;   // 32 ints of pinned host memory: [0..3] counts, [4..7] layer starts, [8..11] aux out, [12..19] aux in
     int opt_overlap = 1;
+    // ---- moving faces (load balance).  Equal layer counts are not equal work: the neighbour count per particle varies
+    // along the tank, and every step runs at the pace of the slowest slab.  With every exchange a rank therefore also
+    // sends {busy time of its last complete step, z0, z1, may-grow}; both ranks at a face apply the same rule to the same
+    // two records (face_shift) and move the face by at most one layer per step towards the busier side.  Nothing else
+    // has to change: the rank that gives a layer away packs it as "beyond the face" (it integrated it, so the data is
+    // current) and keeps its own copy as a ghost layer; ownership is decided by the cell layer at the next sort.  The
+    // local grid is allocated with shift_max spare layers on either side, so z_base never moves.
+    int z0_init = 0, z1_init = 0, shift_max = 0;
+    int opt_rebalance = 1;     // 0 = static faces, 1 = by load, 2 = test pattern (faces oscillate deterministically)
+    int aux_sent[4] = {0, 0, 0, 0};      // what this rank sent with the last exchange
+    int aux_recv[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};  // what it received from below [0] / above [1]
+    bool aux_valid = false;
+    int *d_aux = nullptr;      // device: [0..3] out, [4..7] in from below, [8..11] in from above
+    cudaEvent_t ev_busy[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [step parity][begin, end] of the compute span
+    int busy_recorded[2] = {0, 0};
+    int load_us = 0;
+    uint64_t face_moves = 0;
 };
+
+// The rule both ranks at a face evaluate on the same two records: -1 = the face moves down (the lower rank gives its
+// top layer to the upper rank), +1 = up, 0 = stays.  lo / hi = {load, z0, z1, can_grow} of the lower / upper rank;
+// shift = current offset of the face from the initial plan.
+int face_shift(const int lo[4], const int hi[4], int shift, int shift_max, int mode, uint64_t exchange, int face) {
+    constexpr int kMinLayers = 10;
+    const int layers_lo = lo[2] - lo[1], layers_hi = hi[2] - hi[1];
+    int want = 0;
+    if (mode == 2) {  // test pattern: three exchanges up, three down, phase-shifted per face
+        want = ((exchange + (uint64_t)face) % 6) < 3 ? +1 : -1;
+    } else if (mode == 1 && lo[0] > 0 && hi[0] > 0) {
+        if ((long long)lo[0] * 100 > (long long)hi[0] * 101) want = -1;       // lower rank is busier: it gives a layer away
+        else if ((long long)hi[0] * 100 > (long long)lo[0] * 101) want = +1;
+    }
+    if (want < 0 && (layers_lo <= kMinLayers || shift <= -shift_max || !hi[3])) want = 0;
+    if (want > 0 && (layers_hi <= kMinLayers || shift >= shift_max || !lo[3])) want = 0;
+    return want;
+}
 
 namespace {
 
@@ -169,8 +205,8 @@ Params make_params(const sph_config &c) {
     P.h_win = (double)c.h * (1.0 + 1e-6);
     P.rz_global = P.rz;
     P.z_base = 0;
-    P.own_z0 = 0;
-    P.own_z1 = P.rz;
+    P.own_z0 = P.next_z0 = 0;
+    P.own_z1 = P.next_z1 = P.rz;
     // src/CCPUParticleSimulator.cpp:46-48: m_boxSize.x() / 2.0 and CParticle::h widen to double
     P.hbx = (double)c.box[0] / 2.0;
     P.hby = (double)c.box[1] / 2.0;
@@ -385,8 +421,11 @@ void slab_release(sph_context *c) {
             delete lc;
         }
     }
-    for (void *p : {(void *)s->down_pos, (void *)s->down_vel, (void *)s->up_pos, (void *)s->up_vel, (void *)s->d_counters})
+    for (void *p : {(void *)s->down_pos, (void *)s->down_vel, (void *)s->up_pos, (void *)s->up_vel, (void *)s->d_counters, (void *)s->d_aux})
         if (p) cudaFree(p);
+    for (auto &pair : s->ev_busy)
+        for (cudaEvent_t e : pair)
+            if (e) cudaEventDestroy(e);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     for (cudaEvent_t e : {s->ev_ranges, s->ev_boundary, s->ev_counts, s->ev_comm})
         if (e) cudaEventDestroy(e);
@@ -426,8 +465,10 @@ void slab_pack_begin(sph_context *c, cudaStream_t st) {
 void slab_pack_range(sph_context *c, cudaStream_t st, uint32_t first, uint32_t count) {
     Slab &s = *c->slab;
     const bool has_down = s.rank > 0, has_up = s.rank + 1 < s.world;
-    launch_slab_pack(c->pos_a + first, c->vel_a + first, (int)count, has_down ? s.z0 + 2 : -1, has_up ? s.z1 - 2 : 0x7fffffff,
-                     s.down_pos, s.down_vel, s.up_pos, s.up_vel, s.d_counters, s.cap_face, c->P, st);
+    // thresholds relative to the faces of the COMING step (P.next_z0 / next_z1; equal to z0 / z1 unless a face moves)
+    launch_slab_pack(c->pos_a + first, c->vel_a + first, (int)count, has_down ? c->P.next_z0 + 2 : -1,
+                     has_up ? c->P.next_z1 - 2 : 0x7fffffff, s.down_pos, s.down_vel, s.up_pos, s.up_vel, s.d_counters, s.cap_face,
+                     c->P, st);
     c->kernel_launches += 1;
 }
 
@@ -444,6 +485,7 @@ int local_exchange_counts(sph_context *c, cudaStream_t st, int counts[4]) {
     auto post = [&](LocalEdge &e, int count, const float4 *pos, const float4 *vel) -> int {
         std::lock_guard<std::mutex> g(e.m);
         e.count = count;
+        std::memcpy(e.aux, s.aux_sent, sizeof(e.aux));
         e.pos = pos;
         e.vel = vel;
         CUDA_TRY(c, cudaEventRecord(e.packed, st));
@@ -455,18 +497,20 @@ int local_exchange_counts(sph_context *c, cudaStream_t st, int counts[4]) {
         if (int rc = post(s.local->down[s.rank], counts[0], s.down_pos, s.down_vel)) return rc;
     if (has_up)
         if (int rc = post(s.local->up[s.rank], counts[1], s.up_pos, s.up_vel)) return rc;
-    auto peek = [&](LocalEdge &e, int *count) -> int {
+    auto peek = [&](LocalEdge &e, int *count, int *aux) -> int {
         std::unique_lock<std::mutex> g(e.m);
         e.cv.wait(g, [&] { return e.posted > e.consumed || e.aborted; });
         REQUIRE(c, !e.aborted, SPH_ERR_COMM, "slab (loop-back): a neighbouring rank was destroyed");
         *count = e.count;
+        std::memcpy(aux, e.aux, sizeof(e.aux));
         return SPH_OK;
     };
     counts[2] = counts[3] = 0;
     if (has_down)
-        if (int rc = peek(s.local->up[s.rank - 1], &counts[2])) return rc;
+        if (int rc = peek(s.local->up[s.rank - 1], &counts[2], s.aux_recv[0])) return rc;
     if (has_up)
-        if (int rc = peek(s.local->down[s.rank + 1], &counts[3])) return rc;
+        if (int rc = peek(s.local->down[s.rank + 1], &counts[3], s.aux_recv[1])) return rc;
+    s.aux_valid = true;
     return SPH_OK;
 }
 
@@ -503,19 +547,29 @@ int slab_exchange_counts(sph_context *c, cudaStream_t st, int counts[4]) {
     NcclApi *api = nccl_api(&c->err);
     if (!api) return SPH_ERR_COMM;
     const bool has_down = s.rank > 0, has_up = s.rank + 1 < s.world;
+    std::memcpy(s.h_pinned + 8, s.aux_sent, 4 * sizeof(int));  // the record that travels with the counts
+    CUDA_TRY(c, cudaMemcpyAsync(s.d_aux, s.h_pinned + 8, 4 * sizeof(int), cudaMemcpyHostToDevice, st));
     NCCL_TRY(c, api, api->GroupStart());
     if (has_down) {
         NCCL_TRY(c, api, api->Send(s.d_counters + 0, 1, ncclInt32, s.rank - 1, s.comm, st));
+        NCCL_TRY(c, api, api->Send(s.d_aux, 4, ncclInt32, s.rank - 1, s.comm, st));
         NCCL_TRY(c, api, api->Recv(s.d_counters + 2, 1, ncclInt32, s.rank - 1, s.comm, st));
+        NCCL_TRY(c, api, api->Recv(s.d_aux + 4, 4, ncclInt32, s.rank - 1, s.comm, st));
     }
     if (has_up) {
         NCCL_TRY(c, api, api->Send(s.d_counters + 1, 1, ncclInt32, s.rank + 1, s.comm, st));
+        NCCL_TRY(c, api, api->Send(s.d_aux, 4, ncclInt32, s.rank + 1, s.comm, st));
         NCCL_TRY(c, api, api->Recv(s.d_counters + 3, 1, ncclInt32, s.rank + 1, s.comm, st));
+        NCCL_TRY(c, api, api->Recv(s.d_aux + 8, 4, ncclInt32, s.rank + 1, s.comm, st));
     }
     NCCL_TRY(c, api, api->GroupEnd());
     CUDA_TRY(c, cudaMemcpyAsync(s.h_pinned, s.d_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_pinned + 12, s.d_aux + 4, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(c, cudaEventRecord(s.ev_counts, st));
     CUDA_TRY(c, cudaEventSynchronize(s.ev_counts));  // only this stream's work is waited for
+    std::memcpy(s.aux_recv[0], s.h_pinned + 12, 4 * sizeof(int));
+    std::memcpy(s.aux_recv[1], s.h_pinned + 16, 4 * sizeof(int));
+    s.aux_valid = true;
     counts[0] = s.h_pinned[0];
     counts[1] = s.h_pinned[1];
     counts[2] = has_down ? s.h_pinned[2] : 0;
@@ -560,16 +614,50 @@ int slab_exchange_payload(sph_context *c, cudaStream_t st, const int counts[4], 
     return SPH_OK;
 }
 
-// Blocking exchange on the compute stream: pack the whole owned view, then counts, then payload.
+// Faces of the coming exchange, from the records both neighbours swapped with the previous one (see Slab).
+void slab_plan_faces(sph_context *c) {
+    Slab &s = *c->slab;
+    int nz0 = s.z0, nz1 = s.z1;
+    if (s.opt_rebalance && s.aux_valid && s.world > 1) {
+        if (s.rank > 0)
+            nz0 += face_shift(s.aux_recv[0], s.aux_sent, s.z0 - s.z0_init, s.shift_max, s.opt_rebalance, s.exchanges, s.rank - 1);
+        if (s.rank + 1 < s.world)
+            nz1 += face_shift(s.aux_sent, s.aux_recv[1], s.z1 - s.z1_init, s.shift_max, s.opt_rebalance, s.exchanges, s.rank);
+    }
+    c->P.next_z0 = nz0;
+    c->P.next_z1 = nz1;
+}
+
+// The record that travels with the coming exchange, and the switch to the new faces once it is under way.
+void slab_fill_aux(sph_context *c) {
+    Slab &s = *c->slab;
+    const long long room = (long long)c->cap - 2LL * s.cap_face;
+    s.aux_sent[0] = s.load_us;
+    s.aux_sent[1] = c->P.next_z0;
+    s.aux_sent[2] = c->P.next_z1;
+    s.aux_sent[3] = (long long)s.n_own * 10 < room * 9 ? 1 : 0;
+}
+void slab_adopt_faces(sph_context *c) {
+    Slab &s = *c->slab;
+    if (c->P.next_z0 != s.z0) s.face_moves += 1;
+    if (c->P.next_z1 != s.z1) s.face_moves += 1;
+    s.z0 = c->P.own_z0 = c->P.next_z0;
+    s.z1 = c->P.own_z1 = c->P.next_z1;
+}
+
+// Blocking exchange on the compute stream: pack the whole carried view, then counts, then payload.
 int slab_exchange(sph_context *c) {
     Slab &s = *c->slab;
     int counts[4];
+    slab_plan_faces(c);
+    slab_fill_aux(c);
     slab_pack_begin(c, c->stream);
     slab_pack_range(c, c->stream, c->in_off, s.n_own);
     int rc = slab_exchange_counts(c, c->stream, counts);
     if (rc) return rc;
     rc = slab_exchange_payload(c, c->stream, counts, c->in_off + s.n_own);
     if (rc) return rc;
+    slab_adopt_faces(c);
     c->n = s.n_own + (uint32_t)counts[2] + (uint32_t)counts[3];
     s.have_ghosts = true;
     return SPH_OK;
@@ -578,12 +666,21 @@ int slab_exchange(sph_context *c) {
 // Read back the first particle index of up to 4 local z-layers (cell_start at layer boundaries).
 int slab_layer_starts(sph_context *c, const int layers[4], int out[4]) {
     Slab &s = *c->slab;
+    (void)out;
     const size_t rxy = (size_t)c->P.rx * c->P.xb * c->P.ry;  // sort-key entries per z-layer
     launch_gather4(c->g.cell_start, (size_t)layers[0] * rxy, (size_t)layers[1] * rxy, (size_t)layers[2] * rxy,
                    (size_t)layers[3] * rxy, s.h_pinned + 4, c->stream);  // zero-copy store into the pinned words
     c->kernel_launches += 1;
     CUDA_TRY(c, cudaEventRecord(s.ev_ranges, c->stream));
     return SPH_OK;
+}
+
+// busy time of a complete step (microseconds) from its event pair; the load figure the neighbours compare
+void slab_read_load(Slab &s, int parity) {
+    if (!s.busy_recorded[parity]) return;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s.ev_busy[parity][0], s.ev_busy[parity][1]) == cudaSuccess) s.load_us = (int)(ms * 1000.0f) + 1;
+    s.busy_recorded[parity] = 0;
 }
 
 // Sequential slab step (exchange, then the ordinary step) — reference behaviour for the overlapped variant.
@@ -595,13 +692,19 @@ int slab_step_sequential(sph_context *c, int n_steps, double *ms) {
             int rc = slab_exchange(c);
             if (rc) return rc;
         }
+        c->P.next_z0 = s.z0;  // no face moves inside the step: the next exchange plans them
+        c->P.next_z1 = s.z1;
+        CUDA_TRY(c, cudaEventRecord(s.ev_busy[0][0], c->stream));
         enqueue_step(c);
+        CUDA_TRY(c, cudaEventRecord(s.ev_busy[0][1], c->stream));
+        s.busy_recorded[0] = 1;
         s.have_ghosts = false;
         // the owned particles are the contiguous run of the owned layers in the canonical order
         const int layers[4] = {s.z0 - s.z_base, s.z0 - s.z_base, s.z1 - s.z_base, s.z1 - s.z_base};
         int rc = slab_layer_starts(c, layers, nullptr);
         if (rc) return rc;
         CUDA_TRY(c, cudaEventSynchronize(s.ev_ranges));
+        slab_read_load(s, 0);
         c->in_off = (uint32_t)s.h_pinned[4];
         s.n_own = (uint32_t)(s.h_pinned[6] - s.h_pinned[4]);
     }
@@ -611,13 +714,14 @@ int slab_step_sequential(sph_context *c, int n_steps, double *ms) {
     return rc ? rc : t.finish();
 }
 
-// Overlapped slab step.  After the density pass the forces + integration of the boundary layers (the four owned
-// layers next to each face: two that become the neighbour's ghosts plus two of slack for particles moving towards
-// the face) run on the high-priority communication stream, followed there by the pack and the NCCL exchange for
-// the NEXT step; the interior runs concurrently on the compute stream.  Stream priority matters: without it the
-// interior kernel's queued blocks keep every SM slot and the pack only starts when the interior has drained
-// (measured: profiles/r1_timeline_slab_2gpu.txt).  Ghosts are neither force-evaluated nor integrated, so the
-// received particles can land directly behind the owned run of A while the interior is still being written.
+// Overlapped slab step.  After the density pass the forces + integration of the boundary layers (the owned layers next
+// to each face, down to four layers inside the face this rank will own after the exchange: two that become the
+// neighbour's ghosts plus two of slack for particles moving towards the face) run on the high-priority communication
+// stream, followed there by the pack and the NCCL exchange for the NEXT step; the interior runs concurrently on the
+// compute stream.  Stream priority matters: without it the interior kernel's queued blocks keep every SM slot and
+// the pack only starts when the interior has drained (measured: profiles/r1_timeline_slab_2gpu.txt).  Ghosts are
+// neither force-evaluated nor integrated, so the received particles can land directly behind the owned run of A
+// while the interior is still being written.
 int slab_step_overlapped(sph_context *c, int n_steps, double *ms) {
     Slab &s = *c->slab;
     constexpr int kBoundaryLayers = 4;
@@ -627,15 +731,20 @@ int slab_step_overlapped(sph_context *c, int n_steps, double *ms) {
             int rc = slab_exchange(c);
             if (rc) return rc;
         }
+        const int parity = (int)(c->steps + (uint64_t)k) & 1;
         enqueue_grid(c);
+        slab_plan_faces(c);  // the faces after this step's exchange: the kernels below see them as P.next_z0 / next_z1
         const int l0 = s.z0 - s.z_base, l3 = s.z1 - s.z_base;
-        const int l1 = std::min(l0 + kBoundaryLayers, l3), l2 = std::max(l3 - kBoundaryLayers, l1);
+        const int l1 = std::min(std::max(s.z0, c->P.next_z0) - s.z_base + kBoundaryLayers, l3);
+        const int l2 = std::max(std::min(s.z1, c->P.next_z1) - s.z_base - kBoundaryLayers, l1);
         const int layers[4] = {l0, l1, l2, l3};
         int rc = slab_layer_starts(c, layers, nullptr);
         if (rc) return rc;
+        CUDA_TRY(c, cudaEventRecord(s.ev_busy[parity][0], c->stream));
         enqueue_density(c);  // all local particles: the first ghost layer needs its density too
         CUDA_TRY(c, cudaEventRecord(s.ev_boundary, c->stream));  // "density done": the boundary work may start
         CUDA_TRY(c, cudaEventSynchronize(s.ev_ranges));  // returns while the density pass is still running
+        slab_read_load(s, parity ^ 1);                   // the previous step is complete: its busy time is final
         const int L0 = s.h_pinned[4], L1 = s.h_pinned[5], L2 = s.h_pinned[6], L3 = s.h_pinned[7];
         auto forces_integrate = [&](int i0, int i1, cudaStream_t st) {  // fused forces + walls + integration on [i0, i1)
             launch_forces_mask(c->nb, c->dp, c->nb_count, c->g.key_s, c->g.cell_start, c->acc, i0, i1, c->P, st,
@@ -648,6 +757,9 @@ int slab_step_overlapped(sph_context *c, int n_steps, double *ms) {
         forces_integrate(L2, L3, s.comm_stream);
         // ---- interior: compute stream, concurrently (its blocks fill whatever the boundary work leaves free)
         forces_integrate(L1, L2, c->stream);
+        CUDA_TRY(c, cudaEventRecord(s.ev_busy[parity][1], c->stream));
+        s.busy_recorded[parity] = 1;
+        slab_fill_aux(c);
         slab_pack_begin(c, s.comm_stream);
         slab_pack_range(c, s.comm_stream, (uint32_t)L0, (uint32_t)(L1 - L0));
         slab_pack_range(c, s.comm_stream, (uint32_t)L2, (uint32_t)(L3 - L2));
@@ -658,8 +770,9 @@ int slab_step_overlapped(sph_context *c, int n_steps, double *ms) {
         if (rc) return rc;
         CUDA_TRY(c, cudaEventRecord(s.ev_comm, s.comm_stream));
         CUDA_TRY(c, cudaStreamWaitEvent(c->stream, s.ev_comm, 0));  // the next grid build needs the received tail
-        c->in_off = (uint32_t)L0;
-        s.n_own = (uint32_t)(L3 - L0);
+        slab_adopt_faces(c);
+        c->in_off = (uint32_t)L0;  // carried forward: the run this rank owned during the step (a layer it has just
+        s.n_own = (uint32_t)(L3 - L0);  // given away stays as its own, current, ghost copy; the next sort reclassifies)
         c->n = s.n_own + (uint32_t)counts[2] + (uint32_t)counts[3];
         s.have_ghosts = true;
     }
@@ -1631,6 +1744,11 @@ int sph_set_option(sph_context *c, const char *name, int value) {
         c->slab->opt_overlap = value;
         return SPH_OK;
     }
+    else if (k == "slab_rebalance") {  // 0 static faces, 1 faces follow the load (default), 2 deterministic test pattern
+        REQUIRE(c, c->slab, SPH_ERR_STATE, "sph_set_option: slab_rebalance needs a slab context");
+        c->slab->opt_rebalance = value;
+        return SPH_OK;
+    }
     else return fail(c, SPH_ERR_ARGUMENT, "sph_set_option: unknown option " + k);
     drop_graph(c);
     return SPH_OK;
@@ -1642,6 +1760,8 @@ int sph_get_counter(const sph_context *c, const char *name, uint64_t *value) {
     if (k == "kernel_launches") *value = c->kernel_launches;
     else if (k == "graph_launches") *value = c->graph_launches;
     else if (k == "steps") *value = c->steps;
+    else if (k == "slab_face_moves") *value = c->slab ? c->slab->face_moves : 0;
+    else if (k == "slab_load_us") *value = c->slab ? (uint64_t)c->slab->load_us : 0;
     else if (k == "neighbour_pairs") {  // sum of the per-particle neighbour counts of the last density pass (self included)
         if (cudaSetDevice(c->device) != cudaSuccess) return SPH_ERR_CUDA;
         sph_context *m = const_cast<sph_context *>(c);
@@ -1706,6 +1826,13 @@ int sph_slab_plan(int32_t rz, int32_t world, int32_t rank, int32_t *z0, int32_t 
     return SPH_OK;
 }
 
+int sph_slab_face_shift(const int32_t lower4[4], const int32_t upper4[4], int32_t shift, int32_t shift_max, int32_t mode,
+                        uint64_t exchange, int32_t face) {
+    if (!lower4 || !upper4) return 0;
+    const int lo[4] = {lower4[0], lower4[1], lower4[2], lower4[3]}, hi[4] = {upper4[0], upper4[1], upper4[2], upper4[3]};
+    return face_shift(lo, hi, shift, shift_max, mode, exchange, face);
+}
+
 int sph_slab_create(const sph_config *cfg, sph_context **out) {
     REQUIRE(nullptr, cfg && out, SPH_ERR_ARGUMENT, "sph_slab_create: NULL argument");
     *out = nullptr;
@@ -1713,9 +1840,12 @@ int sph_slab_create(const sph_config *cfg, sph_context **out) {
     REQUIRE(nullptr, cfg->grid_res[2] / cfg->world >= 4, SPH_ERR_ARGUMENT, "sph_slab_create: every slab needs at least 4 z-layers");
     int z0, z1;
     slab_plan(cfg->grid_res[2], cfg->world, cfg->rank, &z0, &z1);
-    const int z_base = std::max(z0 - 2, 0), z_top = std::min(z1 + 2, cfg->grid_res[2]);
+    // the faces may move by up to shift_max layers from this plan (load balance, see Slab): the local grid gets that many
+    // spare layers on either side, so that z_base stays put
+    const int shift_max = cfg->world > 1 ? std::min(std::max((z1 - z0) / 8, 3), 64) : 0;
+    const int z_base = std::max(z0 - 2 - shift_max, 0), z_top = std::min(z1 + 2 + shift_max, cfg->grid_res[2]);
     sph_config local = *cfg;
-    local.grid_res[2] = z_top - z_base;  // owned layers + two ghost layers per interior face
+    local.grid_res[2] = z_top - z_base;  // owned layers + two ghost layers per interior face + room for the faces to move
     local.world = 1;
     int rc = sph_create(&local, out);
     if (rc) return rc;
@@ -1723,15 +1853,16 @@ int sph_slab_create(const sph_config *cfg, sph_context **out) {
     c->cfg = *cfg;
     c->P.rz_global = cfg->grid_res[2];
     c->P.z_base = z_base;
-    c->P.own_z0 = z0;
-    c->P.own_z1 = z1;
+    c->P.own_z0 = c->P.next_z0 = z0;
+    c->P.own_z1 = c->P.next_z1 = z1;
     c->opt_use_graph = 0;  // the particle count changes every step
     Slab *s = new Slab();
     c->slab = s;
     s->rank = cfg->rank;
     s->world = cfg->world;
-    s->z0 = z0;
-    s->z1 = z1;
+    s->z0 = s->z0_init = z0;
+    s->z1 = s->z1_init = z1;
+    s->shift_max = shift_max;
     s->z_base = z_base;
     s->rz_local = z_top - z_base;
     // face buffers: up to 4 layers (2 ghost + 2 of slack for migrants) at 48 particles per cell
@@ -1753,7 +1884,11 @@ int sph_slab_create(const sph_config *cfg, sph_context **out) {
     SLAB_TRY(dalloc(&s->up_vel, (size_t)s->cap_face));
     SLAB_TRY(dalloc(&s->d_counters, (size_t)8));  // [0..3] exchange counts, [4] particles that moved > 2 layers
     SLAB_TRY(cudaMemset(s->d_counters, 0, 8 * sizeof(int)));
-    SLAB_TRY(cudaMallocHost(reinterpret_cast<void **>(&s->h_pinned), 8 * sizeof(int)));
+    SLAB_TRY(cudaMallocHost(reinterpret_cast<void **>(&s->h_pinned), 32 * sizeof(int)));
+    SLAB_TRY(dalloc(&s->d_aux, (size_t)12));
+    SLAB_TRY(cudaMemset(s->d_aux, 0, 12 * sizeof(int)));
+    for (auto &pair : s->ev_busy)
+        for (cudaEvent_t &e : pair) SLAB_TRY(cudaEventCreate(&e));
     // highest priority: the boundary kernels, the pack and NCCL must get SM slots ahead of the interior force kernel
     // that is already filling the device on the compute stream
     int prio_least = 0, prio_greatest = 0;

@@ -26,6 +26,7 @@ struct Params {
     int rz_global;        // z resolution of the whole tank (== rz on a single device)
     int z_base;           // slab mode: global index of local z-layer 0 (0 on a single device)
     int own_z0, own_z1;   // slab mode: owned global layers [own_z0, own_z1) (0 and rz_global on a single device)
+    int next_z0, next_z1; // slab mode: the owned layers AFTER this step's exchange (the faces may move by load, see Slab)
     double hbx, hby, hbz; // double(box)/2.0           (src/CCPUParticleSimulator.cpp:46-48)
     double h_d;           // double(h)
     float h, h2;          // h2 = fl32(h*h) == 0x3b08df0c
@@ -161,13 +162,15 @@ __device__ __forceinline__ void for_each_window_slot(float px, int key, const in
     }
 }
 
-// Slab mode: the overlapped exchange packs only the four owned layers next to each interior face (two that become
-// the neighbour's ghosts plus two of slack).  A particle that starts further inside and ends the step in the outer
-// two layers or beyond would be missed as a ghost / migrant; such particles are counted ("slab_far_movers") and the
-// count must stay 0 (it takes more than two layers = 0.09 m per step, i.e. more than 9 m/s towards the face).
+// Slab mode: the overlapped exchange packs only the owned layers next to each interior face: from the face this
+// rank owns now down to four layers inside the face it will own after the exchange (two that become the neighbour's
+// ghosts plus two of slack; the face may move, see Slab).  A particle that starts further inside and ends the step
+// in the outer two layers or beyond would be missed as a ghost / migrant; such particles are counted
+// ("slab_far_movers") and the count must stay 0 (it takes more than two layers = 0.09 m per step, i.e. more than
+// 9 m/s towards the face).
 __device__ __forceinline__ bool exchange_would_miss(int old_layer, int new_layer, const Params &P) {
-    return (P.own_z0 > 0 && old_layer >= P.own_z0 + 4 && new_layer < P.own_z0 + 2) ||
-           (P.own_z1 < P.rz_global && old_layer < P.own_z1 - 4 && new_layer >= P.own_z1 - 2);
+    return (P.own_z0 > 0 && old_layer >= max(P.own_z0, P.next_z0) + 4 && new_layer < P.next_z0 + 2) ||
+           (P.own_z1 < P.rz_global && old_layer < min(P.own_z1, P.next_z1) - 4 && new_layer >= P.next_z1 - 2);
 }
 
 // ---- walls + integration, shared by k_integrate_collide and the fused force kernel -------------------

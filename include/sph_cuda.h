@@ -214,6 +214,17 @@ int sph_comm_unique_id(uint8_t out[128]);
 int sph_comm_local_id(int32_t world, uint8_t out[128]);
 int sph_slab_plan(int32_t rz, int32_t world, int32_t rank, int32_t *z0, int32_t *z1); /* owned layers [z0, z1) */
 int sph_slab_create(const sph_config *cfg, sph_context **out);
+/* Load balance: equal layer counts are not equal work (the neighbour count varies along the tank) and every step runs at
+ * the pace of the slowest slab, so the faces between slabs MOVE.  With every exchange a rank also sends the record
+ * {busy microseconds of its last complete step, z0, z1, may-grow}; both ranks at a face evaluate this pure function on
+ * the same two records and move the face by its result: -1 = the lower rank gives its top layer to the upper rank,
+ * +1 = the other way, 0 = stay (1 % hysteresis, at least 10 layers per slab, at most shift_max layers from the initial
+ * plan, only into a rank that may grow).  mode 1 = by load, 2 = deterministic test pattern, 0 = never.  A moved face
+ * needs no extra message: the giving rank packs the layer as "beyond the face" and keeps its copy as a ghost layer.
+ * Results do not depend on where the faces are.  Option "slab_rebalance" selects the mode;
+ * counters "slab_face_moves", "slab_load_us". */
+int sph_slab_face_shift(const int32_t lower4[4], const int32_t upper4[4], int32_t shift, int32_t shift_max, int32_t mode,
+                        uint64_t exchange, int32_t face);
 /* out8 = rank, world, z0, z1, first local layer, local layers, owned particles, mean particles sent per step */
 int sph_slab_info(const sph_context *ctx, int32_t out8[8]);
 /* Owned particles in canonical order (not indexed by id; ids are in the records).  Works without slab mode too. */

@@ -29,6 +29,24 @@ def test_slab_plan_rejects_thin_slabs(gws):
         gws.slab_plan(100, 4, 4)
 
 
+def test_face_shift_rule(gws):
+    """The load-balance rule is a pure function that both ranks at a face evaluate on the same two records."""
+    f = gws.slab_face_shift
+    lo, hi = [4000, 0, 400, 1], [3600, 400, 800, 1]          # {load_us, z0, z1, may_grow}
+    assert f(lo, hi) == -1                                    # the lower rank is busier: it gives its top layer away
+    assert f(hi[:1] + lo[1:], lo[:1] + hi[1:]) == +1          # loads swapped: the face moves up
+    assert f([4000, 0, 400, 1], [3980, 400, 800, 1]) == 0     # within the 1 % hysteresis
+    assert f(lo, [3600, 400, 800, 0]) == 0                    # the receiver may not grow
+    assert f(lo, hi, shift=-8, shift_max=8) == 0              # already shift_max layers below the plan
+    assert f([4000, 0, 10, 1], hi) == 0                       # the giving slab is at the minimum thickness
+    assert f([0, 0, 400, 1], hi) == 0 and f(lo, [0, 400, 800, 1]) == 0   # no load measured yet
+    assert f(lo, hi, mode=0) == 0
+    # test pattern: three exchanges up, three down, phase-shifted by the face index; limits still apply
+    assert [f(lo, hi, mode=2, exchange=e, face=0) for e in range(6)] == [1, 1, 1, -1, -1, -1]
+    assert [f(lo, hi, mode=2, exchange=e, face=1) for e in range(6)] == [1, 1, -1, -1, -1, 1]
+    assert f(lo, hi, shift=8, shift_max=8, mode=2, exchange=0) == 0
+
+
 def test_scene_partition_matches_oracle(gws):
     """Each rank keeps exactly the particles whose z-layer (the oracle's key formula) it owns; ids stay global."""
     box = (0.5, 0.3, 1.2)
@@ -120,7 +138,7 @@ def test_single_rank_slab_equals_plain_run(gws):
     assert np.array_equal(b["position"].view(np.uint32), c["position"].view(np.uint32))
 
 
-def run_loopback_slabs(gws, box, world, steps, gravity=None, device_of_rank=None, overlap=True):
+def run_loopback_slabs(gws, box, world, steps, gravity=None, device_of_rank=None, overlap=True, rebalance=None):
     """`world` slab ranks inside this process over the loop-back transport (sph_comm_local_id), each stepped from
     its own host thread like a rank process would; returns the merged owned particles sorted by id + the contexts' info."""
     import threading
@@ -134,6 +152,8 @@ def run_loopback_slabs(gws, box, world, steps, gravity=None, device_of_rank=None
             sim.set_gravity(gravity)
         if not overlap:
             sim.context().set_option("slab_overlap", 0)
+        if rebalance is not None:
+            sim.context().set_option("slab_rebalance", rebalance)
         sims.append(sim)
     errors = []
 
@@ -153,6 +173,8 @@ def run_loopback_slabs(gws, box, world, steps, gravity=None, device_of_rank=None
     parts = [sim.context().download_owned() for sim in sims]
     infos = [sim.context().slab_info() for sim in sims]
     far = [sim.context().counter("slab_far_movers") for sim in sims]
+    for info, sim in zip(infos, sims):
+        info["face_moves"] = sim.context().counter("slab_face_moves")
     merged = np.concatenate(parts)
     merged = merged[np.argsort(merged["id"], kind="stable")]
     for sim in sims:
@@ -204,6 +226,25 @@ def test_loopback_slabs_equal_one_gpu_small_tank_with_migration(gws, world, over
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("overlap", [True, False])
+@pytest.mark.parametrize("rebalance", [2, 1, 0])
+def test_loopback_slabs_with_moving_faces_equal_one_gpu(gws, overlap, rebalance):
+    """The faces between slabs move while the run goes on (load balance): mode 2 drives every face up and down by a
+    deterministic pattern, mode 1 by the measured loads, mode 0 keeps them fixed.  Whatever the faces do, the merged
+    state is bit-identical to the single-GPU run, every particle is owned exactly once, and no particle is missed."""
+    box, steps, g, world = (0.5, 0.5, 2.6), 40, (0.0, -9.80665, 5.0), 3   # 57 cell layers: 19 per slab
+    merged, parts, infos, far = run_loopback_slabs(gws, box, world, steps, gravity=g, overlap=overlap, rebalance=rebalance)
+    assert far == [0] * world
+    moves = sum(i["face_moves"] for i in infos)
+    if rebalance == 2:
+        assert moves >= 2 * 20, moves                      # both faces moved on most steps (counted on both sides)
+    if rebalance == 0:
+        assert moves == 0 and [(i["z0"], i["z1"]) for i in infos] == [(0, 19), (19, 38), (38, 57)]
+    assert [i["z1"] for i in infos[:-1]] == [i["z0"] for i in infos[1:]] and infos[0]["z0"] == 0 and infos[-1]["z1"] == 57
+    assert_same_as_plain(gws, merged, box, steps, gravity=g)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 4])
 def test_loopback_slabs_equal_one_gpu_4m_tank(gws, world):
     """SURVEY.md §8e equivalence case: the 4,000,000-particle tank 4.56 x 4.56 x 9.13 (100 x 100 x 200 cells), k = 2
@@ -212,7 +253,7 @@ def test_loopback_slabs_equal_one_gpu_4m_tank(gws, world):
     box, steps, g = (4.56, 4.56, 9.13), 14, (0.0, -9.80665, 6.0)
     merged, parts, infos, far = run_loopback_slabs(gws, box, world, steps, gravity=g)
     assert merged.shape[0] == 4_000_000 and far == [0] * world
-    assert [i["z1"] - i["z0"] for i in infos] == [200 // world] * world
+    assert sum(i["z1"] - i["z0"] for i in infos) == 200 and infos[0]["z0"] == 0 and infos[-1]["z1"] == 200
     assert migrated_particles(gws, box, world, parts) > 1000
     assert_same_as_plain(gws, merged, box, steps, gravity=g)
 
