@@ -72,16 +72,16 @@ def build(verbose=False):
 
 
 def kernel_source_hash():
-    """sha256 over the kernel library's sources (csrc/*.cu, *.cuh, *.h, Makefile, include/sph_cuda.h): identifies the
-    build an ncu capture belongs to.  (The .so itself is not byte-reproducible across nvcc runs.)"""
+    """sha256 over the sources of the two neighbour kernels an ncu capture describes (csrc/sph_neighbours_v2.cu, the shared
+    device header, the launcher header, the Makefile with the compiler flags): identifies the build a capture belongs
+    to.  (The .so itself is not byte-reproducible across nvcc runs.)"""
     import hashlib
 
     h = hashlib.sha256()
     csrc = os.path.join(_PKG, "csrc")
-    files = sorted(f for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".h")) or f == "Makefile")
-    for path in [os.path.join(csrc, f) for f in files] + [os.path.join(_ROOT, "include", "sph_cuda.h")]:
-        h.update(os.path.basename(path).encode() + b"\0")
-        with open(path, "rb") as f:
+    for name in ("sph_neighbours_v2.cu", "sph_device.cuh", "sph_kernels.h", "Makefile"):
+        h.update(name.encode() + b"\0")
+        with open(os.path.join(csrc, name), "rb") as f:
             h.update(f.read())
     return h.hexdigest()
 

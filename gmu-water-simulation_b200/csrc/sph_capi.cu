@@ -160,8 +160,8 @@ int face_shift(const int lo[4], const int hi[4], int shift, int shift_max, int m
     if (mode == 2) {  // test pattern: three exchanges up, three down, phase-shifted per face
         want = ((exchange + (uint64_t)face) % 6) < 3 ? +1 : -1;
     } else if (mode == 1 && lo[0] > 0 && hi[0] > 0) {
-        if ((long long)lo[0] * 100 > (long long)hi[0] * 101) want = -1;       // lower rank is busier: it gives a layer away
-        else if ((long long)hi[0] * 100 > (long long)lo[0] * 101) want = +1;
+        if ((long long)lo[0] * 1000 > (long long)hi[0] * 1004) want = -1;     // lower rank is busier: it gives a layer away
+        else if ((long long)hi[0] * 1000 > (long long)lo[0] * 1004) want = +1;
     }
     if (want < 0 && (layers_lo <= kMinLayers || shift <= -shift_max || !hi[3])) want = 0;
     if (want > 0 && (layers_hi <= kMinLayers || shift >= shift_max || !lo[3])) want = 0;
@@ -1842,7 +1842,7 @@ int sph_slab_create(const sph_config *cfg, sph_context **out) {
     slab_plan(cfg->grid_res[2], cfg->world, cfg->rank, &z0, &z1);
     // the faces may move by up to shift_max layers from this plan (load balance, see Slab): the local grid gets that many
     // spare layers on either side, so that z_base stays put
-    const int shift_max = cfg->world > 1 ? std::min(std::max((z1 - z0) / 8, 3), 64) : 0;
+    const int shift_max = cfg->world > 1 ? std::min(std::max((z1 - z0) / 5, 3), 128) : 0;
     const int z_base = std::max(z0 - 2 - shift_max, 0), z_top = std::min(z1 + 2 + shift_max, cfg->grid_res[2]);
     sph_config local = *cfg;
     local.grid_res[2] = z_top - z_base;  // owned layers + two ghost layers per interior face + room for the faces to move

@@ -218,7 +218,7 @@ int sph_slab_create(const sph_config *cfg, sph_context **out);
  * the pace of the slowest slab, so the faces between slabs MOVE.  With every exchange a rank also sends the record
  * {busy microseconds of its last complete step, z0, z1, may-grow}; both ranks at a face evaluate this pure function on
  * the same two records and move the face by its result: -1 = the lower rank gives its top layer to the upper rank,
- * +1 = the other way, 0 = stay (1 % hysteresis, at least 10 layers per slab, at most shift_max layers from the initial
+ * +1 = the other way, 0 = stay (0.4 % hysteresis, at least 10 layers per slab, at most shift_max layers from the initial
  * plan, only into a rank that may grow).  mode 1 = by load, 2 = deterministic test pattern, 0 = never.  A moved face
  * needs no extra message: the giving rank packs the layer as "beyond the face" and keeps its copy as a ghost layer.
  * Results do not depend on where the faces are.  Option "slab_rebalance" selects the mode;

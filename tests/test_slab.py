@@ -35,7 +35,7 @@ def test_face_shift_rule(gws):
     lo, hi = [4000, 0, 400, 1], [3600, 400, 800, 1]          # {load_us, z0, z1, may_grow}
     assert f(lo, hi) == -1                                    # the lower rank is busier: it gives its top layer away
     assert f(hi[:1] + lo[1:], lo[:1] + hi[1:]) == +1          # loads swapped: the face moves up
-    assert f([4000, 0, 400, 1], [3980, 400, 800, 1]) == 0     # within the 1 % hysteresis
+    assert f([4000, 0, 400, 1], [3990, 400, 800, 1]) == 0     # within the 0.4 % hysteresis
     assert f(lo, [3600, 400, 800, 0]) == 0                    # the receiver may not grow
     assert f(lo, hi, shift=-8, shift_max=8) == 0              # already shift_max layers below the plan
     assert f([4000, 0, 10, 1], hi) == 0                       # the giving slab is at the minimum thickness
