@@ -162,8 +162,9 @@ def run_loopback_slabs(gws, box, world, steps, gravity=None, device_of_rank=None
             sim.step_many(steps)
         except Exception as exc:  # noqa: BLE001 - reported by the main thread
             errors.append(exc)
+            sim.close()  # destroying the rank wakes the neighbours that wait for it (they fail with a COMM error)
 
-    threads = [threading.Thread(target=work, args=(sim,)) for sim in sims]
+    threads = [threading.Thread(target=work, args=(sim,), daemon=True) for sim in sims]
     for t in threads:
         t.start()
     for t in threads:
