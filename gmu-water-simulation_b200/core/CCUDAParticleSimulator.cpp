@@ -157,7 +157,13 @@ void CCUDAParticleSimulator::step() {
             m_cuda->check(sph_upload_particles(m_cuda->ctx(), reinterpret_cast<const sph_particle *>(m_clParticles.data()),
                                                m_deviceCount), "step upload");
         }
-        CBaseParticleSimulator::step();
+        if (m_scenario == DAM_BREAK && !m_brute && !sampleThisStep()) {
+            // nothing to emit and no phase durations wanted for this step: the five phases as ONE fused device step
+            // (same bits as the phase path; the phase calls remain for sampled steps, the fountain and all-pairs mode)
+            m_cuda->check(sph_step(m_cuda->ctx(), 1, nullptr), "step");
+        } else {
+            CBaseParticleSimulator::step();
+        }
         const bool refresh = (getTotalIteration() + 1) % (unsigned long)m_mirrorStride == 0;
         if (m_mirrorMode == RoundTrip || (m_mirrorMode == Download && refresh)) {
             syncHostMirror();
