@@ -14,8 +14,9 @@
  *   - the render-side classes (QEntity, QTransform, QSphereMesh, materials ...) are empty shells: the
  *     reference only constructs and parents them;
  *   - QVector3D — the ONE piece of arithmetic that lives in Qt — is restated below from Qt 5's
- *     qtbase/src/gui/math3d/qvector3d.h / qvector3d.cpp (5.9 line numbers cited per function; Qt is
- *     not in this image, CMakeLists.txt:60 pins no version, the cited bodies are unchanged 5.5–5.15);
+ *     qtbase/src/gui/math3d/qvector3d.h / qvector3d.cpp, function by function (Qt is not in this image
+ *     and there is no network, so the bodies are quoted from the published Qt 5 sources by function name,
+ *     not by line; CMakeLists.txt:60 pins no version, these bodies are the same throughout Qt 5.5–5.15);
  *   - Qt3DExtras::QCuboidGeometry yields the vertex/index buffers Qt's createCuboidVertexData()
  *     produces for the default 2x2 face resolution: 24 vertices (position 3f, texcoord 2f, normal 3f,
  *     tangent 4f; stride 48 B) at exactly +-extent/2, 36 ushort indices — so the reference's own
@@ -211,15 +212,15 @@ inline unsigned int qNextPowerOfTwo(unsigned int v)
 }
 
 /* ---- QVector3D: restated from Qt 5 (qtbase/src/gui/math3d) ----------------------------------
- * Components are three floats xp, yp, zp (qvector3d.h:139).  All inline operators below are the
- * bodies of qvector3d.h:158-276 (5.9); length / lengthSquared / dotProduct / normalize are the
- * out-of-line bodies of qvector3d.cpp (5.9: length :~620, lengthSquared :~632, normalize :~240,
- * dotProduct :~330).  No operator takes a double. */
+ * Components are three floats xp, yp, zp (private members of QVector3D in qvector3d.h).  The inline operators below
+ * are the bodies of the `inline` definitions at the end of qvector3d.h (operator+=, -=, *=, /=, the friend operators
+ * +, -, *, unary -, /); length / lengthSquared / dotProduct / normalize are the out-of-line bodies of qvector3d.cpp
+ * (QVector3D::length(), ::lengthSquared(), ::dotProduct(), ::normalize()).  No operator takes a double. */
 class QVector3D
 {
 public:
-    QVector3D() : xp(0.0f), yp(0.0f), zp(0.0f) {}                                   /* qvector3d.h:144 */
-    QVector3D(float xpos, float ypos, float zpos) : xp(xpos), yp(ypos), zp(zpos) {}  /* :146 */
+    QVector3D() : xp(0.0f), yp(0.0f), zp(0.0f) {}
+    QVector3D(float xpos, float ypos, float zpos) : xp(xpos), yp(ypos), zp(zpos) {}
 
     float x() const { return xp; }
     float y() const { return yp; }
