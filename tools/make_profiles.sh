@@ -17,5 +17,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 1450 -c 400 --csv -
 # full sections for the two dominant kernels (step 201)
 ncu --set full --clock-control none --import-source on -k regex:"k_density_mask|k_forces_mask" -s 400 -c 2 -o gpurun_out/${TAG}_neighbour_kernels \
     python tools/profile_step.py > gpurun_out/${TAG}_profile_step.log 2>&1
+# summaries of the capture (the same commands work here, without a GPU, on the .ncu-rep that comes back)
+ncu -i gpurun_out/${TAG}_neighbour_kernels.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_neighbour_kernels_raw.csv 2>/dev/null
+python tools/ncu_summary.py gpurun_out/${TAG}_ncu_neighbour_kernels_raw.csv > gpurun_out/${TAG}_ncu_neighbour_kernels.txt
+python tools/kernel_traffic.py gpurun_out/${TAG}_ncu_neighbour_kernels_raw.csv profiles/${TAG}_ncu_neighbour_kernels.txt > gpurun_out/${TAG}_kernel_traffic.json
+python tools/launch_shares.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launch_shares.txt
 python tools/timeline.py > gpurun_out/${TAG}_timeline_graph.txt 2>&1
+# then, here: cp the ${TAG}_* summaries into profiles/ and ${TAG}_kernel_traffic.json to profiles/kernel_traffic.json
 tail -c 600 gpurun_out/${TAG}_bench.json
