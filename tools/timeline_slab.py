@@ -19,6 +19,7 @@ ap.add_argument("--box", type=float, nargs=3, default=[4.56, 4.56, 36.56])
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--preroll", type=int, default=200)
 ap.add_argument("--no-overlap", action="store_true")
+ap.add_argument("--print-rank", type=int, default=0, help="whose timeline to print")
 ap.add_argument("--summary", action="store_true", help="every rank: per-kernel time per step, span and idle time, SM clock while stepping")
 a = ap.parse_args()
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -75,9 +76,9 @@ if a.summary:
             print(json.dumps(r))
     dist.barrier()
     sys.exit(0)
-if rank == 0:
+if rank == a.print_rank:
     ev = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
-    print(f"rank 0 of {world}: {ctx.n} local particles, {ms / 10 * 1e3:.1f} us/step before profiling, {t / a.steps * 1e3:.1f} us/step profiled")
+    print(f"rank {rank} of {world}: {ctx.n} local particles, {ms / 10 * 1e3:.1f} us/step before profiling, {t / a.steps * 1e3:.1f} us/step profiled")
     t0 = ev[0].time_range.start
     cover_end = t0
     idle = 0.0
