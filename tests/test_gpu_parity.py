@@ -480,6 +480,25 @@ def test_full_size_properties_1m(gws):
     assert np.isfinite(rec["position"]).all()
 
 
+def test_cell_ranges_on_a_long_grid_with_many_scan_tiles(gws):
+    """K2 (k_scan) looks back over 512 predecessor tiles per round; a 1.6 x 0.8 x 160 tank has ~9 M bins = more than
+    1 000 tiles, i.e. several rounds.  cell ranges == histogram of the keys, step after step (a race in the look-back
+    shows up as a wrong range somewhere in a few launches)."""
+    sim = gws.Simulator("cuda", (1.6, 0.8, 160.0)).setup_scene()
+    n = sim.n
+    ctx = sim.context()
+    assert 4 * ctx.n_cells > 1000 * 8192
+    for rep in range(12):
+        sim.step_many(3)
+        ctx.update_grid()
+        keys, cs = ctx.keys(), ctx.cell_start()
+        assert cs[0] == 0 and cs[-1] == n, rep
+        assert np.array_equal(np.diff(cs), np.bincount(keys, minlength=ctx.n_cells)), rep
+    perm = ctx.permutation()
+    assert np.array_equal(np.sort(perm), np.arange(n, dtype=np.uint32))
+    assert np.all(np.diff(keys[perm]) >= 0)
+
+
 def test_rollout_statistics_1000_steps(gws):
     """BASELINE north_star: long rollouts are chaotic, so 1000 steps are compared statistically.  Definitions of
     SURVEY.md §8c, sampled every 10 steps (eventLoggerStride): kinetic energy 0.5 m sum|v|^2, centre of mass,
