@@ -207,6 +207,10 @@ Params make_params(const sph_config &c) {
     P.z_base = 0;
     P.own_z0 = P.next_z0 = 0;
     P.own_z1 = P.next_z1 = P.rz;
+    P.kz_lo = 0;
+    P.kz_hi = P.rz;
+    P.dens_key_lo = 0;
+    P.dens_key_hi = 0x7fffffff;
     // src/CCPUParticleSimulator.cpp:46-48: m_boxSize.x() / 2.0 and CParticle::h widen to double
     P.hbx = (double)c.box[0] / 2.0;
     P.hby = (double)c.box[1] / 2.0;
@@ -637,12 +641,31 @@ void slab_fill_aux(sph_context *c) {
     s.aux_sent[2] = c->P.next_z1;
     s.aux_sent[3] = (long long)s.n_own * 10 < room * 9 ? 1 : 0;
 }
+// The part of the local grid the owned layers [z0, z1) put to use.  Particles live in the owned layers and two ghost
+// layers per face; sort keys are confined to one layer more on either side (a particle that is further out is an error
+// the exchange reports, a non-finite one must merely land in a valid bin), the scan covers yet another layer, so every
+// candidate window of every local particle reads scanned bins.  The spare layers that give the faces room to move
+// (shift_max) cost nothing per step this way.  Densities: owned layers + the inner ghost layer of each face.
+void slab_set_layer_windows(sph_context *c) {
+    Slab &s = *c->slab;
+    Params &P = c->P;
+    const int l0 = s.z0 - s.z_base, l3 = s.z1 - s.z_base;
+    const long long plane = (long long)P.rx * P.xb * P.ry;  // sort-key entries per z-layer
+    P.kz_lo = std::max(l0 - 3, 0);
+    P.kz_hi = std::min(l3 + 3, P.rz);
+    P.dens_key_lo = (int)(std::max(l0 - 1, 0) * plane);
+    P.dens_key_hi = (int)std::min<long long>(std::min(l3 + 1, P.rz) * plane, 0x7fffffffLL);
+    const long long lo = std::max(P.kz_lo - 1, 0) * plane, hi = std::min(P.kz_hi + 1, P.rz) * plane + 1;  // bins [lo, hi)
+    c->g.scan_tile0 = (int)(lo / kScanTile);
+    c->g.scan_tiles = std::min(c->g.n_tiles, (int)((hi + kScanTile - 1) / kScanTile)) - c->g.scan_tile0;
+}
 void slab_adopt_faces(sph_context *c) {
     Slab &s = *c->slab;
     if (c->P.next_z0 != s.z0) s.face_moves += 1;
     if (c->P.next_z1 != s.z1) s.face_moves += 1;
     s.z0 = c->P.own_z0 = c->P.next_z0;
     s.z1 = c->P.own_z1 = c->P.next_z1;
+    slab_set_layer_windows(c);
 }
 
 // Blocking exchange on the compute stream: pack the whole carried view, then counts, then payload.
@@ -910,6 +933,8 @@ int sph_create(const sph_config *cfg, sph_context **out) {
     const size_t items = (size_t)c->P.n_cells * (size_t)xb + 1;
     c->g.n_scan_items = (int)items;
     c->g.n_tiles = (int)((items + kScanTile - 1) / kScanTile);
+    c->g.scan_tile0 = 0;
+    c->g.scan_tiles = c->g.n_tiles;
     c->cells_padded = (size_t)c->g.n_tiles * kScanTile;
 
 #define CTX_TRY(call)                       \
@@ -1865,6 +1890,7 @@ int sph_slab_create(const sph_config *cfg, sph_context **out) {
     s->shift_max = shift_max;
     s->z_base = z_base;
     s->rz_local = z_top - z_base;
+    slab_set_layer_windows(c);
     // face buffers: up to 4 layers (2 ghost + 2 of slack for migrants) at 48 particles per cell
     const size_t face = (size_t)cfg->grid_res[0] * cfg->grid_res[1] * 4 * 48;
     s->cap_face = (int)std::min<size_t>(face, c->cap);

@@ -27,6 +27,11 @@ struct Params {
     int z_base;           // slab mode: global index of local z-layer 0 (0 on a single device)
     int own_z0, own_z1;   // slab mode: owned global layers [own_z0, own_z1) (0 and rz_global on a single device)
     int next_z0, next_z1; // slab mode: the owned layers AFTER this step's exchange (the faces may move by load, see Slab)
+    int kz_lo, kz_hi;     // local z-layers [kz_lo, kz_hi) a sort key may name (0 and rz on a single device; in slab mode the
+                          // owned + ghost layers and one more on either side: only those bins are scanned, see launch_scan)
+    int dens_key_lo, dens_key_hi;  // sort keys [lo, hi) whose density is needed (everything on a single device; in slab
+                                   // mode the owned layers and ONE ghost layer per face: the outer ghost layer only lends
+                                   // its positions to the inner one)
     double hbx, hby, hbz; // double(box)/2.0           (src/CCPUParticleSimulator.cpp:46-48)
     double h_d;           // double(h)
     float h, h2;          // h2 = fl32(h*h) == 0x3b08df0c
@@ -80,7 +85,7 @@ __device__ __forceinline__ int cell_key(float4 p, const Params &P) {
     const int cy = cell_coord(p.y, P.hby, P.h_d, P.ry);
     // slab mode: the global layer (clamped like the reference clamps it) is shifted into the local grid
     int cz = cell_coord(p.z, P.hbz, P.h_d, P.rz_global) - P.z_base;
-    cz = min(max(cz, 0), P.rz - 1);
+    cz = min(max(cz, P.kz_lo), P.kz_hi - 1);
     return gx + cy * rxb + cz * rxb * P.ry;
 }
 

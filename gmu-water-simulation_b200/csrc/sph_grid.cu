@@ -46,7 +46,7 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
 }
 
 __global__ void __launch_bounds__(512) k_scan(int *__restrict__ count, int *__restrict__ cell_start, int n_items,
-                                              unsigned long long *__restrict__ status, int n_tiles) {
+                                              unsigned long long *__restrict__ status, int n_tiles, int tile0) {
     __shared__ int s_tile;
     __shared__ int s_warp[16];
     __shared__ int s_prefix;
@@ -54,7 +54,9 @@ __global__ void __launch_bounds__(512) k_scan(int *__restrict__ count, int *__re
     if (tid == 0) s_tile = (int)atomicAdd(status + n_tiles, 1ull);  // ticket: tiles start in order
     __syncthreads();
     const int tile = s_tile;
-    const int base = tile * kScanTile + tid * (4 * kScanVec);
+    // tile0: first tile of the launch (slab mode scans only the layers that can hold particles; the bins below it are
+    // empty, so the running prefix starts at 0 there as well)
+    const int base = (tile0 + tile) * kScanTile + tid * (4 * kScanVec);
 
     // buffers are padded to a multiple of the tile and the padding stays zero
     int4 c[kScanVec];
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(512) k_scan(int *__restrict__ count, int *__re
 
 void launch_scan(const GridBuffers &g, cudaStream_t st) {
     // scan_status is all zero here: zeroed at creation and again by every k_rank_scatter (which follows each scan)
-    k_scan<<<g.n_tiles, 512, 0, st>>>(g.count, g.cell_start, g.n_scan_items, g.scan_status, g.n_tiles);
+    k_scan<<<g.scan_tiles, 512, 0, st>>>(g.count, g.cell_start, g.n_scan_items, g.scan_status, g.n_tiles, g.scan_tile0);
 }
 
 // ---------------------------------------------------------------- K3

@@ -31,6 +31,7 @@ struct GridBuffers {
     unsigned long long *scan_status;  // [tiles + 1]: tile look-back words, last = tile ticket
     int n_scan_items;                 // n_cells * xb + 1
     int n_tiles;
+    int scan_tile0, scan_tiles;       // the tiles launch_scan covers: all of them, or (slab mode) those of the layers in use
 };
 
 // grid build: keys + histogram, exclusive scan, bucket, rank-by-id + SoA reorder

@@ -157,7 +157,10 @@ __global__ void __launch_bounds__(128, 8) k_density_mask(const float *__restrict
     uint2 *const wbase = mask + ((size_t)(i >> 5) * kMaskWords) * 32 + (i & 31);
     int cnt = 0, widx = 0;
     int parity = 0;  // parity of the row start the accumulator halves are currently aligned with
-    for_each_window_slot(px, __ldg(key + i), cell_start, P, [&](const int, const int a, const int b) {
+    const int my_key = __ldg(key + i);
+    // slab mode: the outer ghost layer of a face only lends its positions to the inner one; nobody reads its density
+    const bool wanted = my_key >= P.dens_key_lo && my_key < P.dens_key_hi;
+    if (wanted) for_each_window_slot(px, my_key, cell_start, P, [&](const int, const int a, const int b) {
         if (a >= b) return;
         if ((a ^ parity) & 1) {  // {even, odd} is relative to the row start: swap the halves when its parity flips
             float e, o;
@@ -197,9 +200,10 @@ __global__ void __launch_bounds__(128, 8) k_density_mask(const float *__restrict
     float s_even, s_odd;
     upk(d.acc, s_even, s_odd);
     float sum = s_even + s_odd;  // commutative: independent of which half is which
-    if (!(px < 1.0e17f)) {
+    if (!(px < 1.0e17f) || !wanted) {
         // a particle with a non-finite coordinate (sentinel in xs/ys/zs): in the reference every comparison with NaN
-        // is false, so it has no neighbours at all, not even itself -> density 0 (src/CCPUParticleSimulator.cpp:122-127)
+        // is false, so it has no neighbours at all, not even itself -> density 0 (src/CCPUParticleSimulator.cpp:122-127).
+        // A skipped outer-ghost particle gets the same harmless record.
         sum = 0.0f;
         cnt = 0;
         widx = 0;
