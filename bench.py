@@ -227,6 +227,25 @@ class JsonOut:
         self._out.flush()
 
 
+def bind_host_near_gpu(torch, local):
+    """Pin this process to the CPU cores next to its GPU (NVML's affinity list) BEFORE any pinned host memory is
+    allocated, so that the host mirror lands on that socket's memory (first touch).  What `numactl` / a job launcher
+    does for a rank process; without it eight ranks moving 1.3 GB per step each share whatever socket they woke up
+    on.  Returns what was done for the JSON line; never fatal."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        after = sorted(os.sched_getaffinity(0))
+        return {"cpus_before": before, "cpus": len(after), "first_cpu": after[0], "last_cpu": after[-1], "how": "nvmlDeviceSetCpuAffinity"}
+    except Exception as e:  # no NVML, restricted cpuset, ...: run unbound
+        return {"unbound": f"{type(e).__name__}: {e}"[:120]}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -241,6 +260,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this benchmark has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    host_affinity = bind_host_near_gpu(torch, local) if args.bind_host else {"unbound": "--no-bind-host"}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line, whatever NCCL_DEBUG says
@@ -323,7 +343,7 @@ def run_ours(args):
     value = total_particles * args.steps / (dev_ms * 1e-3)
     if slab:
         finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, dev_ms, wall, launches, total_particles,
-                    clocks, barrier, max_over_ranks, gws, out)
+                    clocks, barrier, max_over_ranks, gws, out, host_affinity)
         return
 
     # ---- per-kernel split ON THE SAME STEPS: the window is replayed from the saved state (same particle order in
@@ -444,6 +464,7 @@ def run_ours(args):
                        "l2": "L2 evicted (256 MiB scratch write, then read back so that no dirty scratch lines remain) before every timed step" if args.flush_l2 else "no eviction"},
             "clocks": clocks.summary(),
             "e2e": e2e,
+            "host_affinity": host_affinity,
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
@@ -501,7 +522,7 @@ def slab_equivalence(gws, dist, rank, world, local, steps=10):
 
 
 def finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, dev_ms, wall, launches, total_particles,
-                clocks, barrier, max_over_ranks, gws, out):
+                clocks, barrier, max_over_ranks, gws, out, host_affinity):
     """N > 1: e2e (upload + step + read-back of the owned particles every step), per-rank slab facts, the JSON line."""
     peak, peak_src = measured_peaks()
     sim.set_mirror_mode(2)  # RoundTrip: every rank uploads its owned 80-byte records, steps, reads them back
@@ -517,6 +538,7 @@ def finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, 
     info["load_us"] = ctx.counter("slab_load_us")
     info["far_movers"] = ctx.counter("slab_far_movers")  # particles the boundary-only exchange would have missed: must be 0
     info["clocks"] = clocks.summary()  # every rank samples its own GPU: the step runs at the pace of the slowest slab
+    info["host_affinity"] = host_affinity
     infos = [None] * world
     dist.all_gather_object(infos, info)
     sim.close()
@@ -536,6 +558,7 @@ def finish_slab(args, sim, ctx, dist, rank, world, local, box, workload, value, 
                        "l2": "no eviction: the per-GPU working set (GBs) is far larger than the 126 MB L2"},
             "clocks": clocks.summary(),
             "clocks_per_rank": [i["clocks"] for i in infos],
+            "host_affinity_per_rank": [i["host_affinity"] for i in infos],
             "e2e": {"value": total_particles * args.e2e_steps / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(80 * total_particles),
                     "d2h_bytes_per_step": int(80 * total_particles), "steps": args.e2e_steps,
                     "ms_per_step": 1e3 * e2e_sec / args.e2e_steps,
@@ -579,6 +602,8 @@ def main():
     ap.add_argument("--slab-rebalance", type=int, default=1, choices=[0, 1],
                     help="N>1: 1 = the faces between slabs follow the measured load (default), 0 = static equal-layer split")
     ap.add_argument("--no-equivalence", action="store_true", help="N>1: skip the 4M-tank slabs == one GPU checksum run")
+    ap.add_argument("--no-bind-host", dest="bind_host", action="store_false",
+                    help="do not pin the process to the CPU cores next to its GPU")
     ap.add_argument("--neighbour-variant", type=int, default=None)
     args = ap.parse_args()
     if args.impl == "reference":
