@@ -171,7 +171,8 @@ int sph_synchronize(sph_context *ctx);
 /* ---- validation taps (all arrays indexed by particle id unless stated) ---- */
 int sph_download_keys(sph_context *ctx, int32_t *keys);                /* cell id of each particle as of the last update_grid */
 int sph_download_permutation(sph_context *ctx, uint32_t *sorted_ids);  /* ids in canonical (cell_id, id) order */
-int sph_download_cell_start(sph_context *ctx, int32_t *cell_start);    /* cells+1 entries */
+int sph_download_cell_start(sph_context *ctx, int32_t *cell_start);    /* cells+1 entries; slab mode: local grid, and only the
+                                                                          layers in use (owned + ghost + 2) are current */
 int sph_download_density_pressure_accel(sph_context *ctx, float *density, float *pressure, float *accel3);
 /* neighbour sets of the grid walk (r2 <= h2, self included): counts[n]; lists (may be NULL) receives the
  * concatenated ascending id lists, particle 0 first; *total = sum(counts) */
