@@ -236,10 +236,12 @@ def test_determinism_and_input_order_independence(gws):
     assert np.array_equal(ra["density"].view(np.uint32), rb["density"].view(np.uint32))
 
 
-def test_brute_force_config(gws):
-    """config 2: all-pairs semantics at 32.5K particles; neighbour sets equal the grid walk and the oracle."""
+@pytest.mark.parametrize("steps", [0, 1, 10, 100])
+def test_brute_force_config(gws, steps):
+    """config 2: all-pairs semantics at 32.5K particles; neighbour sets equal the grid walk and the oracle on the
+    states SURVEY section 8(d) names (steps 0, 1, 10, 100)."""
     box = 1.14
-    o = state_after(box, 3)
+    o = state_after(box, steps)
     assert o.n == 32500
     pos, vel = o.pos, o.vel
     ctx = make_ctx(gws, box, pos, vel)
@@ -254,9 +256,10 @@ def test_brute_force_config(gws):
     ctx.update_grid(); ctx.density_pressure()
     grid_counts, _ = ctx.neighbours(lists=False)
     o.update_grid(); o.update_density_pressure(); o.update_forces()
-    oc, _ = o.neighbours(lists=False)
+    oc, ol = o.neighbours()
     assert np.array_equal(brute_counts, grid_counts)
     assert np.array_equal(brute_counts, oc)
+    assert_neighbour_sets(ctx, oc, ol)  # the grid path's sets (production hit words and the validation walk) on this state
     check_density(o, rho_b, prs_b)
     check_acc(o.acc_sph, o.acc_scale, acc_b)
     o.integrate()
