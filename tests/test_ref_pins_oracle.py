@@ -67,6 +67,18 @@ def test_config0_dam_break_16000_100_steps_bit_identical():
         assert_same_state(r, o, f"step {step}")
 
 
+def test_largest_gui_scene_21296_particles_40_steps_bit_identical():
+    """The largest scene the reference's GUI can create (slider 1.0 -> 21 296 particles, 22^3 cells)."""
+    r = ref_binding.Reference(1.0).setup_scene()
+    o = Oracle(1.0).setup_scene()
+    assert r.n == 21296 and tuple(r.grid_res) == (22, 22, 22)
+    for step in range(40):
+        r.step()
+        o.step()
+        if step % 5 == 4:
+            assert_same_state(r, o, f"step {step}")
+
+
 def test_phase_by_phase_box_0p4():
     """The five phases called one by one (the virtuals CBaseParticleSimulator::step sequences)."""
     r = ref_binding.Reference(0.4).setup_scene()
